@@ -1,0 +1,82 @@
+// common.cuh -- shared host/device helpers of libclica_sm100.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/clica.h"
+
+namespace clica {
+
+// ---- error reporting (thread-local; never throws across the C ABI) ------------------------------
+char* last_error_buffer();   // defined in abi.cu
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CLICA_CUDA_OK(expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return clica::fail((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                               __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define CLICA_REQUIRE(cond, code, ...)                                                            \
+    do {                                                                                          \
+        if (!(cond)) return clica::fail((code), __VA_ARGS__);                                     \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int cc_major = 0;
+    int cc_minor = 0;
+    int ok = 0;
+};
+int get_device_info(DeviceInfo* out);   // cached per device; defined in abi.cu
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 4-byte and 16-byte cp.async with zero-fill of the bytes beyond src_bytes (LDGSTS).
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace clica

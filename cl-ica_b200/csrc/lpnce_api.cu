@@ -1,0 +1,453 @@
+// lpnce_api.cu -- C-ABI entry points of the fused Lp-InfoNCE loss (see include/clica.h) plus the small
+// O(B*d) kernels around the pair-walking kernels of lpnce_kernels.cuh: finalize (merge split partials,
+// positive pair, per-item loss, the three means), prep (per-anchor backward coefficients) and reduce
+// (sum split partials, add the positive-pair gradient).
+#include "lpnce_kernels.cuh"
+
+namespace clica {
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// scalar |t|^p and d|t|^p/dt for the O(B*d) positive-pair work (accurate libm paths for generic p)
+__device__ __forceinline__ float abs_pow(float t, float p) {
+    float a = fabsf(t);
+    if (p == 1.f) return a;
+    if (p == 2.f) return a * a;
+    if (p == 3.f) return a * a * a;
+    if (p == 4.f) { float u = a * a; return u * u; }
+    return a == 0.f ? 0.f : exp2f(p * log2f(a));
+}
+__device__ __forceinline__ float dabs_pow(float t, float p) {   // 0 at t == 0 (torch masks it too)
+    if (t == 0.f) return 0.f;
+    float a = fabsf(t);
+    float m;
+    if (p == 1.f) m = 1.f;
+    else if (p == 2.f) m = 2.f * a;
+    else if (p == 3.f) m = 3.f * a * a;
+    else if (p == 4.f) m = 4.f * a * a * a;
+    else m = p * exp2f((p - 1.f) * log2f(a));
+    return copysignf(m, t);
+}
+
+struct FinParams {
+    const float* part_m; const float* part_s; int part_stride; int nsplit;
+    const float* z1; int ld1; const float* z2; int ld2;
+    int B; int M; int d; float p; float tau; float alpha; int include_pos;
+    float* loss_i; float* lse; float* pos; float* scalars;
+    double* block_sums; int* counter;
+};
+
+__global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v_loss = 0.f, v_pos = 0.f, v_lse = 0.f;
+    if (i < q.B) {
+        float ps = 0.f;
+        const float* a = q.z1 + (size_t)i * q.ld1;
+        const float* b = q.z2 + (size_t)i * q.ld2;
+        for (int c = 0; c < q.d; ++c) ps += abs_pow(a[c] - b[c], q.p);
+        const float coef = kLog2e / q.tau;
+        float M = q.part_m[i];
+        for (int sidx = 1; sidx < q.nsplit; ++sidx) M = fmaxf(M, q.part_m[(size_t)sidx * q.part_stride + i]);
+        const float xp = -ps * coef;
+        if (q.include_pos) M = fmaxf(M, xp);
+        float S = q.include_pos ? exp2f(xp - M) : 0.f;
+        for (int sidx = 0; sidx < q.nsplit; ++sidx)
+            S += q.part_s[(size_t)sidx * q.part_stride + i] * exp2f(q.part_m[(size_t)sidx * q.part_stride + i] - M);
+        float l = (M + log2f(S)) * kLn2;
+        if (!q.include_pos) l -= logf((float)q.M);
+        const float li = 2.f * (q.alpha * ps / q.tau + (1.f - q.alpha) * l);
+        q.loss_i[i] = li;
+        q.lse[i] = l;
+        q.pos[i] = ps;
+        v_loss = li; v_pos = ps / q.tau; v_lse = l;
+    }
+    // deterministic: per-block sums, then the last block to finish adds them in block order
+    __shared__ float red[3][8];
+    __shared__ int is_last;
+    v_loss = warp_sum(v_loss); v_pos = warp_sum(v_pos); v_lse = warp_sum(v_lse);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = v_loss; red[1][warp] = v_pos; red[2][warp] = v_lse; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0, s1 = 0, s2 = 0;
+        for (int w = 0; w < 8; ++w) { s0 += red[0][w]; s1 += red[1][w]; s2 += red[2][w]; }
+        q.block_sums[3 * blockIdx.x + 0] = s0;
+        q.block_sums[3 * blockIdx.x + 1] = s1;
+        q.block_sums[3 * blockIdx.x + 2] = s2;
+        __threadfence();
+        is_last = (atomicAdd(q.counter, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        volatile double* bs = q.block_sums;
+        double s0 = 0, s1 = 0, s2 = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) { s0 += bs[3 * b]; s1 += bs[3 * b + 1]; s2 += bs[3 * b + 2]; }
+        q.scalars[0] = (float)(s0 / q.B);
+        q.scalars[1] = (float)(s1 / q.B);
+        q.scalars[2] = (float)(s2 / q.B);
+    }
+}
+
+// per-anchor coefficients of the backward:  L2 = log2-domain (un-shifted) lse, E = 2 gl (1-alpha)/tau,
+// CP = 2 gl (alpha - (1-alpha) w+)/tau,  gl_i = g_mean * inv_count + g_loss_i[i]
+struct PrepParams {
+    const float* lse; const float* pos; const float* g_mean; const float* g_loss_i;
+    int n; float inv_count; float shift; float tau; float alpha; int include_pos;
+    float* L2; float* E; float* CP;   // CP nullable (then pos is not read)
+    float default_g;                  // used when g_mean == nullptr
+};
+__global__ void lpnce_prep_kernel(const PrepParams q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n) return;
+    float gl = (q.g_mean ? *q.g_mean : q.default_g) * q.inv_count;
+    if (q.g_loss_i) gl += q.g_loss_i[i];
+    const float l2 = (q.lse[i] + q.shift) * kLog2e;
+    if (q.L2) q.L2[i] = l2;
+    if (q.E) q.E[i] = 2.f * gl * (1.f - q.alpha) / q.tau;
+    if (q.CP) {
+        const float wpos = q.include_pos ? exp2f(-q.pos[i] * (kLog2e / q.tau) - l2) : 0.f;
+        q.CP[i] = 2.f * gl * (q.alpha - (1.f - q.alpha) * wpos) / q.tau;
+    }
+}
+
+// g_out[row, c] = p * ( E[row] * sum_s partA[s][row][c] + sum_s partB[s][row][c] ) + CP[row] * G'(z1 - z2)
+struct ReduceParams {
+    const float* partA; int nsA; int rowsA;   // anchor role, scaled by E; nullable
+    const float* partB; int nsB; int rowsB;   // column role, already weighted; nullable
+    const float* E; const float* CP;          // CP nullable (no positive term)
+    const float* z1; int ld1; const float* z2; int ld2;
+    float* g_out; int ldg; float* g_z2; int ldg2;   // both nullable
+    int rows; int d; int TW; float p;
+};
+__global__ void lpnce_reduce_kernel(const ReduceParams q) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)q.rows * q.d) return;
+    const int row = (int)(idx / q.d), c = (int)(idx - (long long)row * q.d);
+    float g = 0.f;
+    if (q.partA) {
+        float a = 0.f;
+        for (int s = 0; s < q.nsA; ++s) a += q.partA[((size_t)s * q.rowsA + row) * q.TW + c];
+        g = q.E[row] * a;
+    }
+    if (q.partB) {
+        float b = 0.f;
+        for (int s = 0; s < q.nsB; ++s) b += q.partB[((size_t)s * q.rowsB + row) * q.TW + c];
+        g += b;
+    }
+    g *= q.p;
+    if (q.CP) {
+        const float gp = q.CP[row] * dabs_pow(q.z1[(size_t)row * q.ld1 + c] - q.z2[(size_t)row * q.ld2 + c], q.p);
+        g += gp;
+        if (q.g_z2) q.g_z2[(size_t)row * q.ldg2 + c] = -gp;
+    }
+    if (q.g_out) q.g_out[(size_t)row * q.ldg + c] = g;
+}
+
+// ---- host-side planning ---------------------------------------------------------------------------
+const int kDpList[] = {2, 3, 4, 5, 8, 12, 16, 20};
+int pick_dp(int d) {
+    const int need = (d + 1) / 2;
+    for (int v : kDpList) if (v >= need) return v;
+    return -1;
+}
+int p_code(float p) {
+    if (p == 1.f) return 1;
+    if (p == 2.f) return 2;
+    if (p == 3.f) return 3;
+    if (p == 4.f) return 4;
+    return 0;
+}
+
+struct SplitPlan { int row_tiles; int tiles_per_split; int nsplit; };
+SplitPlan plan_splits(int rows, int rows_cta, int MS, int sm_count, int ctas_per_sm) {
+    SplitPlan pl;
+    pl.row_tiles = ceil_div(rows, rows_cta);
+    const int col_tiles = ceil_div(MS, kTN);
+    int want = (sm_count * ctas_per_sm) / (pl.row_tiles > 0 ? pl.row_tiles : 1);
+    if (want < 1) want = 1;
+    if (want > col_tiles) want = col_tiles;
+    if (want > 64) want = 64;
+    pl.tiles_per_split = ceil_div(col_tiles, want);
+    pl.nsplit = ceil_div(col_tiles, pl.tiles_per_split);
+    return pl;
+}
+// register-limited occupancy estimate, used only to size the grid (any value is correct)
+int ctas_per_sm_guess(int DP, int R, bool bwd) {
+    const int regs = (bwd ? 4 : 2) * DP * R + 4 * DP + 40;
+    int n = 65536 / (kThreads * (regs > 32 ? regs : 32));
+    return n < 1 ? 1 : (n > 4 ? 4 : n);
+}
+SplitPlan plan_fwd(int B, int M, int DP, int sms) {
+    const int R = fwd_rows_per_thread(DP);
+    return plan_splits(B, rows_per_cta(R), M, sms, ctas_per_sm_guess(DP, R, false));
+}
+SplitPlan plan_bwd(int rows, int MS, int DP, int sms) {
+    const int R = bwd_rows_per_thread(DP);
+    return plan_splits(rows, rows_per_cta(R), MS, sms, ctas_per_sm_guess(DP, R, true));
+}
+
+int dispatch_fwd(int pc, int DP, const FwdParams& q, dim3 g, cudaStream_t s) {
+    switch (pc) {
+        case 1: return launch_fwd_p1(DP, q, g, s);
+        case 2: return launch_fwd_p2(DP, q, g, s);
+        case 3: return launch_fwd_p3(DP, q, g, s);
+        case 4: return launch_fwd_p4(DP, q, g, s);
+        default: return launch_fwd_p0(DP, q, g, s);
+    }
+}
+int dispatch_bwd(int pc, int DP, const BwdParams& q, dim3 g, cudaStream_t s) {
+    switch (pc) {
+        case 1: return launch_bwd_p1(DP, q, g, s);
+        case 2: return launch_bwd_p2(DP, q, g, s);
+        case 3: return launch_bwd_p3(DP, q, g, s);
+        case 4: return launch_bwd_p4(DP, q, g, s);
+        default: return launch_bwd_p0(DP, q, g, s);
+    }
+}
+
+int check_common(int B, int M, int d, float p, float tau, int use_pow, int* DP, DeviceInfo* di) {
+    CLICA_REQUIRE(B >= 1 && M >= 1 && d >= 1, CLICA_E_BADARG, "lpnce: need B, M, d >= 1 (got %d, %d, %d)", B, M, d);
+    CLICA_REQUIRE(tau > 0.f, CLICA_E_BADARG, "lpnce: tau must be > 0 (got %g)", (double)tau);
+    CLICA_REQUIRE(p >= 1.f, CLICA_E_UNSUPPORTED,
+                  "lpnce: p = %g < 1 (losses.py:433-442 branch) is not implemented by the CUDA path", (double)p);
+    CLICA_REQUIRE(use_pow == 1, CLICA_E_UNSUPPORTED, "lpnce: pow=False is not implemented by the CUDA path");
+    *DP = pick_dp(d);
+    CLICA_REQUIRE(*DP > 0, CLICA_E_UNSUPPORTED, "lpnce: feature width d = %d > 40 is not implemented yet", d);
+    int rc = get_device_info(di);
+    if (rc) return rc;
+    return 0;
+}
+
+struct FwdWs { int* counter; double* block_sums; float* part_m; float* part_s; size_t bytes; };
+FwdWs carve_fwd(void* ws, int B, int nsplit) {
+    FwdWs w;
+    char* p = (char*)ws;
+    size_t off = 0;
+    w.counter = (int*)(p + off); off += 16;
+    w.block_sums = (double*)(p + off); off += align_up(3ull * ceil_div(B, 256) * sizeof(double), 16);
+    w.part_m = (float*)(p + off); off += align_up((size_t)nsplit * B * sizeof(float), 16);
+    w.part_s = (float*)(p + off); off += align_up((size_t)nsplit * B * sizeof(float), 16);
+    w.bytes = off;
+    return w;
+}
+
+struct BwdWs { float* L2; float* E; float* CP; float* partA; float* partB; size_t bytes; };
+// nL = entries of L2/E (B for the plain backward, M for the sharded one)
+BwdWs carve_bwd(void* ws, int nL, int B, int rowsA, int nsA, int rowsB, int nsB, int TW) {
+    BwdWs w;
+    char* p = (char*)ws;
+    size_t off = 0;
+    w.L2 = (float*)(p + off); off += align_up((size_t)nL * sizeof(float), 16);
+    w.E = (float*)(p + off); off += align_up((size_t)nL * sizeof(float), 16);
+    w.CP = (float*)(p + off); off += align_up((size_t)B * sizeof(float), 16);
+    w.partA = (float*)(p + off); off += align_up((size_t)nsA * rowsA * TW * sizeof(float), 16);
+    w.partB = (float*)(p + off); off += align_up((size_t)nsB * rowsB * TW * sizeof(float), 16);
+    w.bytes = off;
+    return w;
+}
+
+inline int is_flat16(const float* S, int ldS, int d, int DP) {
+    return (d == 2 * DP) && (ldS == d) && (((uintptr_t)S & 15u) == 0);
+}
+
+}  // namespace
+}  // namespace clica
+
+using namespace clica;
+
+extern "C" size_t clica_lpnce_workspace_bytes(int B, int M, int d) {
+    DeviceInfo di;
+    int DP = pick_dp(d);
+    if (B < 1 || M < 1 || DP < 0 || get_device_info(&di)) return 0;
+    SplitPlan pl = plan_fwd(B, M, DP, di.sm_count);
+    return carve_fwd(nullptr, B, pl.nsplit).bytes;
+}
+
+extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
+                               int B, int M, int d, float p, float tau, float alpha, int include_pos,
+                               int use_pow, float* loss_i, float* lse, float* pos, float* scalars3,
+                               void* ws, size_t ws_bytes, void* stream) {
+    int DP; DeviceInfo di;
+    int rc = check_common(B, M, d, p, tau, use_pow, &DP, &di);
+    if (rc) return rc;
+    CLICA_REQUIRE(z1 && z2 && z3 && loss_i && lse && pos && scalars3 && ws, CLICA_E_BADARG, "lpnce_fwd: null pointer");
+    CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d, CLICA_E_BADARG, "lpnce_fwd: leading dimension < d");
+    CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_fwd: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    SplitPlan pl = plan_fwd(B, M, DP, di.sm_count);
+    FwdWs w = carve_fwd(ws, B, pl.nsplit);
+    CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_fwd: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+
+    FwdParams q;
+    q.O = z1; q.ldO = ld1; q.BO = B; q.S = z3; q.ldS = ld3; q.MS = M; q.d = d;
+    q.coef = kLog2e / tau; q.pg = p;
+    q.tiles_per_split = pl.tiles_per_split; q.flat16 = is_flat16(z3, ld3, d, DP);
+    q.part_m = w.part_m; q.part_s = w.part_s; q.part_stride = B; q.counter = w.counter;
+    rc = dispatch_fwd(p_code(p), DP, q, dim3(pl.row_tiles, pl.nsplit, 1), st);
+    if (rc) return rc;
+
+    FinParams f;
+    f.part_m = w.part_m; f.part_s = w.part_s; f.part_stride = B; f.nsplit = pl.nsplit;
+    f.z1 = z1; f.ld1 = ld1; f.z2 = z2; f.ld2 = ld2; f.B = B; f.M = M; f.d = d; f.p = p; f.tau = tau;
+    f.alpha = alpha; f.include_pos = include_pos;
+    f.loss_i = loss_i; f.lse = lse; f.pos = pos; f.scalars = scalars3;
+    f.block_sums = w.block_sums; f.counter = w.counter;
+    lpnce_finalize_kernel<<<ceil_div(B, 256), 256, 0, st>>>(f);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t clica_lpnce_bwd_workspace_bytes(int B, int M, int d) {
+    DeviceInfo di;
+    int DP = pick_dp(d);
+    if (B < 1 || M < 1 || DP < 0 || get_device_info(&di)) return 0;
+    SplitPlan a = plan_bwd(B, M, DP, di.sm_count), b = plan_bwd(M, B, DP, di.sm_count);
+    return carve_bwd(nullptr, B, B, B, a.nsplit, M, b.nsplit, 2 * DP).bytes;
+}
+
+extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
+                               int B, int M, int d, float p, float tau, float alpha, int include_pos,
+                               int use_pow, const float* lse, const float* pos, const float* g_mean,
+                               const float* g_loss_i, float* g_z1, int ldg1, float* g_z2, int ldg2,
+                               float* g_z3, int ldg3, void* ws, size_t ws_bytes, void* stream) {
+    int DP; DeviceInfo di;
+    int rc = check_common(B, M, d, p, tau, use_pow, &DP, &di);
+    if (rc) return rc;
+    CLICA_REQUIRE(z1 && z2 && z3 && lse && pos && ws, CLICA_E_BADARG, "lpnce_bwd: null pointer");
+    CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d, CLICA_E_BADARG, "lpnce_bwd: leading dimension < d");
+    CLICA_REQUIRE((!g_z1 || ldg1 >= d) && (!g_z2 || ldg2 >= d) && (!g_z3 || ldg3 >= d), CLICA_E_BADARG,
+                  "lpnce_bwd: gradient leading dimension < d");
+    CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_bwd: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int TW = 2 * DP;
+    SplitPlan pa = plan_bwd(B, M, DP, di.sm_count), pb = plan_bwd(M, B, DP, di.sm_count);
+    BwdWs w = carve_bwd(ws, B, B, B, pa.nsplit, M, pb.nsplit, TW);
+    CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_bwd: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+
+    PrepParams pp;
+    pp.lse = lse; pp.pos = pos; pp.g_mean = g_mean; pp.g_loss_i = g_loss_i; pp.n = B;
+    pp.inv_count = 1.f / (float)B; pp.shift = include_pos ? 0.f : logf((float)M);
+    pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
+    pp.L2 = w.L2; pp.E = w.E; pp.CP = w.CP; pp.default_g = 0.f;
+    lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp);
+    CLICA_CUDA_OK(cudaGetLastError());
+
+    const bool needA = (g_z1 != nullptr), needB = (g_z3 != nullptr);
+    if (needA || needB) {
+        BwdParams q;
+        q.d = d; q.coef = kLog2e / tau; q.pg = p; q.nroles = 0;
+        int gx = 0, gy = 0;
+        if (needA) {   // anchors own, negatives stream
+            BwdRole& r = q.role[q.nroles++];
+            r.O = z1; r.ldO = ld1; r.BO = B; r.S = z3; r.ldS = ld3; r.MS = M;
+            r.LO = w.L2; r.LS = nullptr; r.ES = nullptr;
+            r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z3, ld3, d, DP);
+            r.part = w.partA; r.part_rows = B; r.row_tiles = pa.row_tiles;
+            gx = max(gx, pa.row_tiles); gy = max(gy, pa.nsplit);
+        }
+        if (needB) {   // negatives own, anchors (with their lse and coefficient) stream
+            BwdRole& r = q.role[q.nroles++];
+            r.O = z3; r.ldO = ld3; r.BO = M; r.S = z1; r.ldS = ld1; r.MS = B;
+            r.LO = nullptr; r.LS = w.L2; r.ES = w.E;
+            r.tiles_per_split = pb.tiles_per_split; r.nsplit = pb.nsplit; r.flat16 = is_flat16(z1, ld1, d, DP);
+            r.part = w.partB; r.part_rows = M; r.row_tiles = pb.row_tiles;
+            gx = max(gx, pb.row_tiles); gy = max(gy, pb.nsplit);
+        }
+        rc = dispatch_bwd(p_code(p), DP, q, dim3(gx, gy, q.nroles), st);
+        if (rc) return rc;
+    }
+    if (g_z1 || g_z2) {
+        ReduceParams r;
+        r.partA = needA ? w.partA : nullptr; r.nsA = pa.nsplit; r.rowsA = B;
+        r.partB = nullptr; r.nsB = 0; r.rowsB = 0;
+        r.E = w.E; r.CP = w.CP; r.z1 = z1; r.ld1 = ld1; r.z2 = z2; r.ld2 = ld2;
+        r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
+        r.rows = B; r.d = d; r.TW = TW; r.p = p;
+        const long long n = (long long)B * d;
+        lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r);
+        CLICA_CUDA_OK(cudaGetLastError());
+    }
+    if (g_z3) {
+        ReduceParams r;
+        r.partA = nullptr; r.nsA = 0; r.rowsA = 0;
+        r.partB = w.partB; r.nsB = pb.nsplit; r.rowsB = M;
+        r.E = nullptr; r.CP = nullptr; r.z1 = nullptr; r.ld1 = 0; r.z2 = nullptr; r.ld2 = 0;
+        r.g_out = g_z3; r.ldg = ldg3; r.g_z2 = nullptr; r.ldg2 = 0;
+        r.rows = M; r.d = d; r.TW = TW; r.p = p;
+        const long long n = (long long)M * d;
+        lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r);
+        CLICA_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" size_t clica_lpnce_bwd_sharded_workspace_bytes(int B, int M, int d) {
+    DeviceInfo di;
+    int DP = pick_dp(d);
+    if (B < 1 || M < 1 || DP < 0 || get_device_info(&di)) return 0;
+    SplitPlan a = plan_bwd(B, M, DP, di.sm_count);
+    return carve_bwd(nullptr, M, B, B, a.nsplit, B, a.nsplit, 2 * DP).bytes;
+}
+
+extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const float* z2_local, int ld2,
+                                       const float* z_all, int ld3, const float* lse_all,
+                                       const float* pos_local, int B, int M, int d, int row0, float p,
+                                       float tau, float alpha, int include_pos, const float* g_scale,
+                                       float* g_z1, int ldg1, float* g_z2, int ldg2,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    int DP; DeviceInfo di;
+    int rc = check_common(B, M, d, p, tau, 1, &DP, &di);
+    if (rc) return rc;
+    CLICA_REQUIRE(z1_local && z2_local && z_all && lse_all && pos_local && g_z1 && ws, CLICA_E_BADARG,
+                  "lpnce_bwd_sharded: null pointer");
+    CLICA_REQUIRE(row0 >= 0 && row0 + B <= M, CLICA_E_BADARG, "lpnce_bwd_sharded: rows [%d, %d) outside [0, %d)", row0, row0 + B, M);
+    CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d && ldg1 >= d && (!g_z2 || ldg2 >= d), CLICA_E_BADARG,
+                  "lpnce_bwd_sharded: leading dimension < d");
+    CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_bwd_sharded: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int TW = 2 * DP;
+    SplitPlan pa = plan_bwd(B, M, DP, di.sm_count);
+    BwdWs w = carve_bwd(ws, M, B, B, pa.nsplit, B, pa.nsplit, TW);
+    CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_bwd_sharded: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+
+    // coefficients of every global anchor (they all stream through the column-role pass) ...
+    PrepParams pp;
+    pp.lse = lse_all; pp.pos = nullptr; pp.g_mean = g_scale; pp.g_loss_i = nullptr; pp.n = M;
+    pp.inv_count = 1.f / (float)M; pp.shift = include_pos ? 0.f : logf((float)M);
+    pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
+    pp.L2 = w.L2; pp.E = w.E; pp.CP = nullptr; pp.default_g = 1.f;
+    lpnce_prep_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pp);
+    CLICA_CUDA_OK(cudaGetLastError());
+    // ... and the positive-pair coefficient of the local rows
+    pp.lse = lse_all + row0; pp.pos = pos_local; pp.n = B; pp.L2 = nullptr; pp.E = nullptr; pp.CP = w.CP;
+    lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp);
+    CLICA_CUDA_OK(cudaGetLastError());
+
+    BwdParams q;
+    q.d = d; q.coef = kLog2e / tau; q.pg = p; q.nroles = 2;
+    const int flat = is_flat16(z_all, ld3, d, DP);
+    for (int k = 0; k < 2; ++k) {
+        BwdRole& r = q.role[k];
+        r.O = z1_local; r.ldO = ld1; r.BO = B; r.S = z_all; r.ldS = ld3; r.MS = M;
+        r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = flat;
+        r.part_rows = B; r.row_tiles = pa.row_tiles;
+    }
+    q.role[0].LO = w.L2 + row0; q.role[0].LS = nullptr; q.role[0].ES = nullptr; q.role[0].part = w.partA;   // local rows as anchors
+    q.role[1].LO = nullptr; q.role[1].LS = w.L2; q.role[1].ES = w.E; q.role[1].part = w.partB;             // local rows as negatives
+    rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 2), st);
+    if (rc) return rc;
+
+    ReduceParams r;
+    r.partA = w.partA; r.nsA = pa.nsplit; r.rowsA = B;
+    r.partB = w.partB; r.nsB = pa.nsplit; r.rowsB = B;
+    r.E = w.E + row0; r.CP = w.CP; r.z1 = z1_local; r.ld1 = ld1; r.z2 = z2_local; r.ld2 = ld2;
+    r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
+    r.rows = B; r.d = d; r.TW = TW; r.p = p;
+    const long long n = (long long)B * d;
+    lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,457 @@
+// lpnce_kernels.cuh -- fused pairwise-Lp-distance + InfoNCE (soft-max cross-entropy) kernels.
+//
+// Replaces /root/reference/losses.py:443-477 (+ :506-510) and the autograd graph behind it.
+// The reference materialises B x M x d and B x M temporaries; here neither exists:
+//
+//   "row-owner" scheme -- every thread OWNS R rows of one operand (their d features live in registers,
+//   pre-negated), all threads of a CTA walk the rows of the other operand, which are STREAMED through
+//   shared memory in cp.async double-buffered tiles and read with warp-broadcast 128-bit loads.  A pair
+//   (owner row, streamed row) is therefore handled entirely by one thread:
+//     forward : D = sum_c |s_c - o_c|^p  ->  online log-sum-exp (lazy re-scaling, logits <= 0)
+//     backward: w = exp2(-D*coef - lse2) ->  g_owner += w * d|t|^p/dt      (distance recomputed)
+//   so there are no shuffles, no atomics and no cross-thread reductions in the inner loops.  The
+//   backward runs the same kernel twice with the operands' roles swapped (anchors own / negatives own);
+//   this is also exactly the row-sharded multi-GPU formulation.
+//   Feature PAIRS are processed with the sm_100 packed-fp32 instructions (add.f32x2 / fma.rn.f32x2 via
+//   __fadd2_rn / __ffma2_rn): half the issue slots per pair-element.
+//   Column splits (grid.y) fill all SMs; split partials are merged by a small finalize / reduce kernel
+//   in a fixed order, so results are deterministic.
+#pragma once
+#include "common.cuh"
+
+#include <math.h>
+
+namespace clica {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTN = 128;          // streamed rows per shared-memory tile
+constexpr int kCW = 4;            // warps of a CTA that split the streamed rows of a tile
+constexpr float kRescale = 24.f;  // lazy soft-max re-scaling threshold (log2 units)
+
+// rows owned per thread: 2 while the register budget allows it
+constexpr int fwd_rows_per_thread(int DP) { return DP <= 12 ? 2 : 1; }
+constexpr int bwd_rows_per_thread(int DP) { return DP <= 5 ? 2 : 1; }
+constexpr int rows_per_cta(int R) { return 32 * R * (kWarps / kCW); }
+
+inline size_t fwd_smem_bytes(int DP, int R) {
+    size_t tiles = 2ull * kTN * 2 * DP * sizeof(float);
+    size_t merge = 2ull * kWarps * R * 32 * sizeof(float);
+    return tiles > merge ? tiles : merge;
+}
+inline size_t bwd_smem_bytes(int DP, int R) {
+    size_t tiles = 2ull * (kTN * 2 * DP + 2 * kTN) * sizeof(float);
+    size_t merge = (size_t)(kCW - 1) * (kWarps / kCW) * R * DP * 32 * sizeof(float2);
+    return tiles > merge ? tiles : merge;
+}
+
+struct FwdParams {
+    const float* O; int ldO; int BO;     // owner rows (anchors z1)
+    const float* S; int ldS; int MS;     // streamed rows (negatives z3)
+    int d; float coef; float pg;         // coef = log2(e)/tau, pg = p (generic-exponent kernels)
+    int tiles_per_split; int flat16;
+    float* part_m; float* part_s; int part_stride;   // [nsplit][part_stride]
+    int* counter;                        // zeroed here for the finalize kernel's last-block reduction
+};
+
+// w(owner i, streamed j) = ES[j] * exp2( -D * coef - LO[i] - LS[j] );  gacc_i += w * G'(s_j - o_i)/p
+struct BwdRole {
+    const float* O; int ldO; int BO;
+    const float* S; int ldS; int MS;
+    const float* LO;                   // owner log2-domain lse (nullable -> 0)
+    const float* LS; const float* ES;  // streamed log2-domain lse and coefficient (both or neither)
+    int tiles_per_split; int nsplit; int flat16;
+    float* part; int part_rows;        // [nsplit][part_rows][2*DP]
+    int row_tiles;
+};
+struct BwdParams {
+    BwdRole role[2];
+    int nroles;
+    int d; float coef; float pg;
+};
+
+#ifdef __CUDACC__
+
+// ---- per-exponent arithmetic ----------------------------------------------------------------------
+// P = 1,2,3,4: multiply-only; P = 0: generic real exponent through lg2/ex2 (pg = p).
+template <int P>
+struct Lp {
+    // acc += |t|^p for the two features packed in t
+    static __device__ __forceinline__ float2 accum(float2 t, float2 acc, float pg) {
+        if constexpr (P == 2) {
+            return __ffma2_rn(t, t, acc);
+        } else if constexpr (P == 1) {
+            acc.x += fabsf(t.x);
+            acc.y += fabsf(t.y);
+            return acc;
+        } else if constexpr (P == 3) {
+            float2 u = __fmul2_rn(t, t);
+            acc.x = fmaf(fabsf(t.x), u.x, acc.x);
+            acc.y = fmaf(fabsf(t.y), u.y, acc.y);
+            return acc;
+        } else if constexpr (P == 4) {
+            float2 u = __fmul2_rn(t, t);
+            return __ffma2_rn(u, u, acc);
+        } else {
+            acc.x += ex2_approx(pg * lg2_approx(fabsf(t.x)));   // |0|^p: lg2 -> -inf -> ex2 -> 0
+            acc.y += ex2_approx(pg * lg2_approx(fabsf(t.y)));
+            return acc;
+        }
+    }
+    // g += w * sign(t)|t|^(p-1)     (the factor p is applied once, by the reduce kernel)
+    static __device__ __forceinline__ float2 grad(float w, float2 t, float2 g, float pg) {
+        if constexpr (P == 2) {
+            return __ffma2_rn(make_float2(w, w), t, g);
+        } else if constexpr (P == 1) {
+            // sign(0) = 0: a zero difference contributes exactly nothing (torch masks it too)
+            g.x += (t.x == 0.f) ? 0.f : copysignf(w, t.x);
+            g.y += (t.y == 0.f) ? 0.f : copysignf(w, t.y);
+            return g;
+        } else if constexpr (P == 3) {
+            g.x = fmaf(w, t.x * fabsf(t.x), g.x);
+            g.y = fmaf(w, t.y * fabsf(t.y), g.y);
+            return g;
+        } else if constexpr (P == 4) {
+            float2 u = __fmul2_rn(t, t);
+            return __ffma2_rn(make_float2(w, w), __fmul2_rn(u, t), g);
+        } else {
+            float ax = ex2_approx((pg - 1.f) * lg2_approx(fabsf(t.x)));
+            float ay = ex2_approx((pg - 1.f) * lg2_approx(fabsf(t.y)));
+            g.x = fmaf(w, copysignf(ax, t.x), g.x);   // p > 1 here: |0|^(p-1) = 0
+            g.y = fmaf(w, copysignf(ay, t.y), g.y);
+            return g;
+        }
+    }
+};
+
+// ---- streamed-tile loader -------------------------------------------------------------------------
+// dst: [kTN][2*DP] floats.  Rows >= MS and features >= d are zero-filled.
+template <int DP>
+__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ S, int ldS, int MS,
+                                          int d, int k0, int flat16, int tid) {
+    constexpr int W = 2 * DP;
+    if (flat16) {   // d == W, ldS == d, 16B-aligned base: the tile is one contiguous chunk
+        constexpr int G = kTN * W / 4;
+        const long long total = (long long)MS * d;
+        for (int g = tid; g < G; g += kThreads) {
+            long long e = (long long)k0 * d + 4ll * g;
+            long long rem = total - e;
+            int bytes = rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0);
+            cp_async_16(dst + 4 * g, bytes > 0 ? (const void*)(S + e) : (const void*)S, bytes);
+        }
+    } else {
+        for (int e = tid; e < kTN * W; e += kThreads) {
+            int k = e / W, c = e - k * W;
+            bool ok = (k0 + k < MS) && (c < d);
+            cp_async_4(dst + e, ok ? (const void*)(S + (size_t)(k0 + k) * ldS + c) : (const void*)S, ok ? 4 : 0);
+        }
+    }
+}
+
+// own rows, negated and zero-padded, into registers
+template <int DP, int R>
+__device__ __forceinline__ void load_owner_rows(float2 (&na)[R][DP], const float* __restrict__ O, int ldO,
+                                                int BO, int d, int row_base, int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row_base + r * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) {
+            float v0 = 0.f, v1 = 0.f;
+            if (row < BO) {
+                if (2 * c < d) v0 = __ldg(O + (size_t)row * ldO + 2 * c);
+                if (2 * c + 1 < d) v1 = __ldg(O + (size_t)row * ldO + 2 * c + 1);
+            }
+            na[r][c] = make_float2(-v0, -v1);
+        }
+    }
+}
+
+// ================================ forward ==========================================================
+template <int P, int DP, int R, int CW>
+__global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) {
+    constexpr int RW = kWarps / CW;
+    constexpr int ROWS = 32 * R * RW;
+    constexpr int TW = 2 * DP;                 // floats per streamed row in shared memory
+    constexpr int CPW = kTN / CW;              // streamed rows per warp per tile
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rw = warp / CW, cw = warp % CW;
+    const int row_base = blockIdx.x * ROWS + rw * (32 * R);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *q.counter = 0;
+
+    float2 na[R][DP];
+    load_owner_rows<DP, R>(na, q.O, q.ldO, q.BO, q.d, row_base, lane);
+
+    const int ntiles = (q.MS + kTN - 1) / kTN;
+    const int t0 = blockIdx.y * q.tiles_per_split;
+    const int t1 = min(ntiles, t0 + q.tiles_per_split);
+    load_tile<DP>(smem, q.S, q.ldS, q.MS, q.d, t0 * kTN, q.flat16, tid);
+    cp_async_commit();
+
+    float m[R], s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { m[r] = 0.f; s[r] = 0.f; }
+
+    for (int t = t0; t < t1; ++t) {
+        const int stage = (t - t0) & 1;
+        if (t + 1 < t1) {
+            load_tile<DP>(smem + (stage ^ 1) * kTN * TW, q.S, q.ldS, q.MS, q.d, (t + 1) * kTN, q.flat16, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* tile = smem + stage * kTN * TW;
+        const int nvalid = min(kTN, q.MS - t * kTN);
+        if (t == t0) {
+            // reference point of the lazy soft-max: the logit of the first streamed row of this split
+            const float2* b = reinterpret_cast<const float2*>(tile);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < DP; ++c) acc = Lp<P>::accum(__fadd2_rn(b[c], na[r][c]), acc, q.pg);
+                m[r] = -(acc.x + acc.y) * q.coef;
+            }
+        }
+        const int c_end = min(cw * CPW + CPW, nvalid);
+        for (int kk = cw * CPW; kk < c_end; kk += 2) {
+            // rows kk, kk+1 are contiguous: 2*TW floats = DP float4 (kk even -> 16B aligned)
+            const float4* bq = reinterpret_cast<const float4*>(tile + kk * TW);
+            float2 bb[2 * DP];
+#pragma unroll
+            for (int c = 0; c < DP; ++c) {
+                float4 v = bq[c];
+                bb[2 * c] = make_float2(v.x, v.y);
+                bb[2 * c + 1] = make_float2(v.z, v.w);
+            }
+            const bool has1 = (kk + 1 < c_end);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < DP; ++c) {
+                    a0 = Lp<P>::accum(__fadd2_rn(bb[c], na[r][c]), a0, q.pg);
+                    a1 = Lp<P>::accum(__fadd2_rn(bb[DP + c], na[r][c]), a1, q.pg);
+                }
+                const float D0 = a0.x + a0.y;
+                const float D1 = has1 ? (a1.x + a1.y) : INFINITY;
+                float x0 = fmaf(D0, -q.coef, -m[r]);
+                float x1 = fmaf(D1, -q.coef, -m[r]);
+                const float hi = fmaxf(x0, x1);
+                if (hi > kRescale) {   // rare: a much closer negative than the reference point appeared
+                    const float mn = m[r] + hi;
+                    s[r] *= ex2_approx(m[r] - mn);
+                    m[r] = mn;
+                    x0 = fmaf(D0, -q.coef, -mn);
+                    x1 = fmaf(D1, -q.coef, -mn);
+                }
+                s[r] += ex2_approx(x0) + ex2_approx(x1);
+            }
+        }
+        __syncthreads();
+    }
+
+    // merge the CW column-warps that share a row group, then publish this split's partial (m, s)
+    float* mm = smem;                       // [kWarps][R][32]
+    float* ms = smem + kWarps * R * 32;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        mm[(warp * R + r) * 32 + lane] = m[r];
+        ms[(warp * R + r) * 32 + lane] = s[r];
+    }
+    __syncthreads();
+    if (cw == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float M = m[r];
+#pragma unroll
+            for (int w2 = 1; w2 < CW; ++w2) M = fmaxf(M, mm[((warp + w2) * R + r) * 32 + lane]);
+            float Ssum = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < CW; ++w2) {
+                const int idx = ((warp + w2) * R + r) * 32 + lane;
+                Ssum += ms[idx] * exp2f(mm[idx] - M);
+            }
+            const int row = row_base + r * 32 + lane;
+            if (row < q.BO) {
+                q.part_m[(size_t)blockIdx.y * q.part_stride + row] = M;
+                q.part_s[(size_t)blockIdx.y * q.part_stride + row] = Ssum;
+            }
+        }
+    }
+}
+
+// ================================ backward =========================================================
+template <int P, int DP, int R, int CW>
+__global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) {
+    constexpr int RW = kWarps / CW;
+    constexpr int ROWS = 32 * R * RW;
+    constexpr int TW = 2 * DP;
+    constexpr int CPW = kTN / CW;
+    constexpr int TILE_FLOATS = kTN * TW + 2 * kTN;   // features + (LS, ES) per streamed row
+    extern __shared__ __align__(16) float smem[];
+    const BwdRole& ro = q.role[blockIdx.z];
+    if ((int)blockIdx.x >= ro.row_tiles || (int)blockIdx.y >= ro.nsplit) return;
+    const bool has_ss = (ro.LS != nullptr);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rw = warp / CW, cw = warp % CW;
+    const int row_base = blockIdx.x * ROWS + rw * (32 * R);
+
+    float2 na[R][DP];
+    float2 gacc[R][DP];
+    float lo[R];
+    load_owner_rows<DP, R>(na, ro.O, ro.ldO, ro.BO, q.d, row_base, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row_base + r * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) gacc[r][c] = make_float2(0.f, 0.f);
+        lo[r] = (ro.LO != nullptr && row < ro.BO) ? __ldg(ro.LO + row) : 0.f;
+    }
+
+    const int ntiles = (ro.MS + kTN - 1) / kTN;
+    const int t0 = blockIdx.y * ro.tiles_per_split;
+    const int t1 = min(ntiles, t0 + ro.tiles_per_split);
+
+    auto issue_tile = [&](int stage, int t) {
+        float* dst = smem + stage * TILE_FLOATS;
+        load_tile<DP>(dst, ro.S, ro.ldS, ro.MS, q.d, t * kTN, ro.flat16, tid);
+        if (has_ss && tid < kTN) {
+            const int j = t * kTN + tid;
+            const bool ok = j < ro.MS;
+            float* sdst = dst + kTN * TW + 2 * tid;
+            cp_async_4(sdst, ok ? (const void*)(ro.LS + j) : (const void*)ro.LS, ok ? 4 : 0);
+            cp_async_4(sdst + 1, ok ? (const void*)(ro.ES + j) : (const void*)ro.ES, ok ? 4 : 0);
+        }
+        cp_async_commit();
+    };
+    issue_tile(0, t0);
+
+    for (int t = t0; t < t1; ++t) {
+        const int stage = (t - t0) & 1;
+        if (t + 1 < t1) { issue_tile(stage ^ 1, t + 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float* tile = smem + stage * TILE_FLOATS;
+        const float2* ss = reinterpret_cast<const float2*>(tile + kTN * TW);
+        const int nvalid = min(kTN, ro.MS - t * kTN);
+        const int c_end = min(cw * CPW + CPW, nvalid);
+        for (int kk = cw * CPW; kk < c_end; kk += 2) {
+            const float4* bq = reinterpret_cast<const float4*>(tile + kk * TW);
+            float2 bb[2 * DP];
+#pragma unroll
+            for (int c = 0; c < DP; ++c) {
+                float4 v = bq[c];
+                bb[2 * c] = make_float2(v.x, v.y);
+                bb[2 * c + 1] = make_float2(v.z, v.w);
+            }
+            const bool has1 = (kk + 1 < c_end);
+            float ls0 = 0.f, ls1 = 0.f, es0 = 1.f, es1 = has1 ? 1.f : 0.f;
+            if (has_ss) {
+                const float4 sv = *reinterpret_cast<const float4*>(ss + kk);   // (LS0, ES0, LS1, ES1)
+                ls0 = sv.x; es0 = sv.y; ls1 = sv.z; es1 = has1 ? sv.w : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < DP; ++c) {
+                    a0 = Lp<P>::accum(__fadd2_rn(bb[c], na[r][c]), a0, q.pg);
+                    a1 = Lp<P>::accum(__fadd2_rn(bb[DP + c], na[r][c]), a1, q.pg);
+                }
+                const float w0 = es0 * ex2_approx(fmaf(a0.x + a0.y, -q.coef, -(lo[r] + ls0)));
+                const float w1 = es1 * ex2_approx(fmaf(a1.x + a1.y, -q.coef, -(lo[r] + ls1)));
+#pragma unroll
+                for (int c = 0; c < DP; ++c) {
+                    gacc[r][c] = Lp<P>::grad(w0, __fadd2_rn(bb[c], na[r][c]), gacc[r][c], q.pg);
+                    gacc[r][c] = Lp<P>::grad(w1, __fadd2_rn(bb[DP + c], na[r][c]), gacc[r][c], q.pg);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // sum the CW column-warps of each row group (fixed order), write this split's partial
+    float2* buf = reinterpret_cast<float2*>(smem);   // [(CW-1) * RW][R][DP][32]
+    if (cw > 0) {
+        const int slot = (cw - 1) * RW + rw;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < DP; ++c) buf[((slot * R + r) * DP + c) * 32 + lane] = gacc[r][c];
+    }
+    __syncthreads();
+    if (cw == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row_base + r * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < DP; ++c) {
+                float2 g = gacc[r][c];
+#pragma unroll
+                for (int w2 = 1; w2 < CW; ++w2) {
+                    const float2 o = buf[((((w2 - 1) * RW + rw) * R + r) * DP + c) * 32 + lane];
+                    g.x += o.x; g.y += o.y;
+                }
+                if (row < ro.BO)
+                    *reinterpret_cast<float2*>(ro.part + ((size_t)blockIdx.y * ro.part_rows + row) * TW + 2 * c) = g;
+            }
+        }
+    }
+}
+
+// ---- launch helpers (instantiated once per exponent, see lpnce_inst.cuh) ---------------------------
+template <int P, int DP>
+int launch_fwd_pd(const FwdParams& q, dim3 grid, cudaStream_t st) {
+    constexpr int R = fwd_rows_per_thread(DP);
+    auto kern = lpnce_fwd_kernel<P, DP, R, kCW>;
+    const size_t smem = fwd_smem_bytes(DP, R);
+    if (smem > 48 * 1024)
+        CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(q);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+template <int P, int DP>
+int launch_bwd_pd(const BwdParams& q, dim3 grid, cudaStream_t st) {
+    constexpr int R = bwd_rows_per_thread(DP);
+    auto kern = lpnce_bwd_kernel<P, DP, R, kCW>;
+    const size_t smem = bwd_smem_bytes(DP, R);
+    if (smem > 48 * 1024)
+        CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(q);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+#define CLICA_DISPATCH_DP(P_, DPV, FN, ...)                                                \
+    switch (DPV) {                                                                         \
+        case 2: return FN<P_, 2>(__VA_ARGS__);                                             \
+        case 3: return FN<P_, 3>(__VA_ARGS__);                                             \
+        case 4: return FN<P_, 4>(__VA_ARGS__);                                             \
+        case 5: return FN<P_, 5>(__VA_ARGS__);                                             \
+        case 8: return FN<P_, 8>(__VA_ARGS__);                                             \
+        case 12: return FN<P_, 12>(__VA_ARGS__);                                           \
+        case 16: return FN<P_, 16>(__VA_ARGS__);                                           \
+        case 20: return FN<P_, 20>(__VA_ARGS__);                                           \
+        default: return clica::fail(CLICA_E_UNSUPPORTED, "no register-resident kernel for DP=%d", DPV); \
+    }
+
+#endif  // __CUDACC__
+
+// one translation unit per exponent keeps the build parallel: lpnce_p{0,1,2,3,4}.cu define these
+int launch_fwd_p0(int DP, const FwdParams& q, dim3 g, cudaStream_t s);
+int launch_fwd_p1(int DP, const FwdParams& q, dim3 g, cudaStream_t s);
+int launch_fwd_p2(int DP, const FwdParams& q, dim3 g, cudaStream_t s);
+int launch_fwd_p3(int DP, const FwdParams& q, dim3 g, cudaStream_t s);
+int launch_fwd_p4(int DP, const FwdParams& q, dim3 g, cudaStream_t s);
+int launch_bwd_p0(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
+int launch_bwd_p1(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
+int launch_bwd_p2(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
+int launch_bwd_p3(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
+int launch_bwd_p4(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
+
+}  // namespace clica

@@ -1,0 +1,219 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (device memory, streams: PyTorch; math: CUDA).
+
+* :func:`lp_infonce`     <- reference ``losses.py:443-477`` forward + autograd backward
+* :func:`mlp_forward`    <- reference ``encoders.py:36-58`` (Linear+LeakyReLU stack) forward + backward
+* :func:`adam_step`      <- ``torch.optim.Adam.step`` for a parameter list (main_mlp.py:283)
+
+All tensors must be CUDA fp32; anything else raises.  Nothing here synchronises the host.
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+# ---- per-(device, stream) scratch ---------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
+    """A cached byte buffer, private to (device, current stream, tag); grows geometrically.
+
+    Stream-ordered reuse is safe because every kernel that touches it is launched on that stream."""
+    stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index, stream, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_rows(t: torch.Tensor, what: str) -> torch.Tensor:
+    """fp32 CUDA matrix with unit column stride (row stride may exceed the width: strided views are fine)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor (the CUDA path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
+    if t.dim() != 2:
+        raise RuntimeError(f"{what}: expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.shape[0] > 1 and (t.stride(1) != 1 or t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    elif t.shape[0] <= 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ---- fused Lp-InfoNCE loss ----------------------------------------------------------------------------
+class _LpInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, z3, p, tau, alpha, include_pos):
+        lib = _lib.load()
+        z1, z2, z3 = _as_rows(z1, "z1_rec"), _as_rows(z2, "z2_con_z1_rec"), _as_rows(z3, "z3_rec")
+        B, d = z1.shape
+        M = z3.shape[0]
+        if z2.shape != (B, d) or z3.shape[1] != d:
+            raise RuntimeError(f"shape mismatch: z1 {tuple(z1.shape)}, z2 {tuple(z2.shape)}, z3 {tuple(z3.shape)}")
+        dev = z1.device
+        with torch.cuda.device(dev):
+            out = torch.empty(3 * B + 3, dtype=torch.float32, device=dev)
+            loss_i, lse, pos, scal = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:]
+            nbytes = lib.clica_lpnce_workspace_bytes(B, M, d)
+            ws = _workspace(nbytes, dev, "lpnce")
+            rc = lib.clica_lpnce_fwd(z1.data_ptr(), _ld(z1), z2.data_ptr(), _ld(z2), z3.data_ptr(), _ld(z3),
+                                     B, M, d, float(p), float(tau), float(alpha), int(include_pos), 1,
+                                     loss_i.data_ptr(), lse.data_ptr(), pos.data_ptr(), scal.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            _lib.check(rc, "clica_lpnce_fwd")
+        ctx.save_for_backward(z1, z2, z3, lse, pos)
+        ctx.cfg = (float(p), float(tau), float(alpha), int(include_pos))
+        ctx.set_materialize_grads(False)
+        mean, pos_mean, neg_mean = scal[0], scal[1], scal[2]
+        ctx.mark_non_differentiable(pos_mean, neg_mean)
+        return mean, loss_i, pos_mean, neg_mean
+
+    @staticmethod
+    def backward(ctx, g_mean, g_loss_i, _g_pos, _g_neg):
+        lib = _lib.load()
+        z1, z2, z3, lse, pos = ctx.saved_tensors
+        p, tau, alpha, include_pos = ctx.cfg
+        B, d = z1.shape
+        M = z3.shape[0]
+        dev = z1.device
+        need1, need2, need3 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need1 or need2 or need3) or (g_mean is None and g_loss_i is None):
+            return (None,) * 7
+        with torch.cuda.device(dev):
+            g1 = torch.empty_like(z1, memory_format=torch.contiguous_format) if need1 else None
+            g2 = torch.empty_like(z2, memory_format=torch.contiguous_format) if need2 else None
+            g3 = torch.empty_like(z3, memory_format=torch.contiguous_format) if need3 else None
+            if g_mean is not None:
+                g_mean = g_mean.to(device=dev, dtype=torch.float32).contiguous()
+            if g_loss_i is not None:
+                g_loss_i = g_loss_i.to(device=dev, dtype=torch.float32).contiguous()
+            nbytes = lib.clica_lpnce_bwd_workspace_bytes(B, M, d)
+            ws = _workspace(nbytes, dev, "lpnce_bwd")
+            rc = lib.clica_lpnce_bwd(z1.data_ptr(), _ld(z1), z2.data_ptr(), _ld(z2), z3.data_ptr(), _ld(z3),
+                                     B, M, d, p, tau, alpha, include_pos, 1, lse.data_ptr(), pos.data_ptr(),
+                                     _ptr(g_mean), _ptr(g_loss_i), _ptr(g1), d, _ptr(g2), d, _ptr(g3), d,
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            _lib.check(rc, "clica_lpnce_bwd")
+        return g1, g2, g3, None, None, None, None
+
+
+def lp_infonce(z1_rec, z2_rec, z3_rec, p, tau=1.0, alpha=0.5, include_pos=True):
+    """Fused Lp-InfoNCE. Returns ``(mean, per_item[B], pos_mean, neg_mean)``; mean and per_item carry grad."""
+    return _LpInfoNCE.apply(z1_rec, z2_rec, z3_rec, p, tau, alpha, include_pos)
+
+
+# ---- encoder stack ------------------------------------------------------------------------------------
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (_vp * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class _MLP(torch.autograd.Function):
+    """y = Linear_{L-1}( LeakyReLU( ... LeakyReLU(Linear_0(x)) ) ) through clica_mlp_fwd / clica_mlp_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, slope, mode, *params):
+        lib = _lib.load()
+        x = _as_rows(x, "encoder input").contiguous()
+        L = len(params) // 2
+        Ws = [params[2 * l] for l in range(L)]
+        bs = [params[2 * l + 1] for l in range(L)]
+        widths = [Ws[0].shape[1]] + [W.shape[0] for W in Ws]
+        if x.shape[1] != widths[0]:
+            raise RuntimeError(f"encoder input has {x.shape[1]} features, first Linear expects {widths[0]}")
+        for l, (W, b) in enumerate(zip(Ws, bs)):
+            if not (W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and W.shape[1] == widths[l]):
+                raise RuntimeError(f"layer {l}: weight must be a contiguous CUDA fp32 [{widths[l + 1]}, {widths[l]}] tensor")
+            if b is None or not (b.is_cuda and b.dtype == torch.float32 and b.is_contiguous()):
+                raise RuntimeError(f"layer {l}: bias must be a contiguous CUDA fp32 tensor")
+        M = x.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            acts = [x] + [torch.empty((M, w), dtype=torch.float32, device=dev) for w in widths[1:]]
+            cw = (ctypes.c_int * (L + 1))(*widths)
+            nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
+            ws = _workspace(nbytes, dev, "mlp")
+            rc = lib.clica_mlp_fwd(L, cw, _ptr_array(Ws), _ptr_array(bs), _ptr_array(acts), M, float(slope),
+                                   int(mode), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            _lib.check(rc, "clica_mlp_fwd")
+        ctx.save_for_backward(*acts[:-1], *Ws)
+        ctx.cfg = (L, widths, float(slope), int(mode), [b is not None for b in bs])
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        L, widths, slope, mode, _ = ctx.cfg
+        saved = ctx.saved_tensors
+        acts, Ws = list(saved[:L]), list(saved[L:])
+        M = acts[0].shape[0]
+        dev = gy.device
+        gy = gy.contiguous()
+        with torch.cuda.device(dev):
+            dWs = [torch.empty_like(W) for W in Ws]
+            dbs = [torch.empty(W.shape[0], dtype=torch.float32, device=dev) for W in Ws]
+            g_in = torch.empty_like(acts[0]) if ctx.needs_input_grad[0] else None
+            cw = (ctypes.c_int * (L + 1))(*widths)
+            nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
+            ws = _workspace(nbytes, dev, "mlp")
+            rc = lib.clica_mlp_bwd(L, cw, _ptr_array(Ws), _ptr_array(acts), gy.data_ptr(), _ptr_array(dWs),
+                                   _ptr_array(dbs), _ptr(g_in), M, slope, mode, ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(dev))
+            _lib.check(rc, "clica_mlp_bwd")
+        grads = []
+        for l in range(L):
+            grads.append(dWs[l] if ctx.needs_input_grad[3 + 2 * l] else None)
+            grads.append(dbs[l] if ctx.needs_input_grad[4 + 2 * l] else None)
+        return (g_in, None, None, *grads)
+
+
+def mlp_forward(x, weights: List[torch.Tensor], biases: List[torch.Tensor], slope: float = 0.01,
+                mode: Optional[int] = None):
+    """Linear+LeakyReLU(slope) stack, identity after the last Linear. Differentiable in x, weights, biases."""
+    if mode is None:
+        mode = _lib.gemm_mode_from_env()
+    flat = []
+    for W, b in zip(weights, biases):
+        flat += [W, b]
+    return _MLP.apply(x, slope, mode, *flat)
+
+
+# ---- fused Adam -----------------------------------------------------------------------------------------
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """One fused multi-tensor Adam update (in place) for contiguous CUDA fp32 tensors on one device."""
+    lib = _lib.load()
+    if not params:
+        return
+    dev = params[0].device
+    for group in (params, grads, exp_avgs, exp_avg_sqs):
+        for t in group:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == dev):
+                raise RuntimeError("adam_step: all tensors must be contiguous CUDA fp32 on one device")
+    n = len(params)
+    numel = (ctypes.c_int64 * n)(*[p.numel() for p in params])
+    with torch.cuda.device(dev):
+        rc = lib.clica_adam_step(n, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs),
+                                 _ptr_array(exp_avg_sqs), numel, float(lr), float(beta1), float(beta2),
+                                 float(eps), int(step), float(grad_scale), _stream_ptr(dev))
+        _lib.check(rc, "clica_adam_step")

@@ -1,0 +1,38 @@
+"""Run the reference's byte-identical ``main_mlp.py`` against the drop-in ``losses`` / ``encoders`` modules.
+
+    python -m clica_b200.launch --reference /root/reference -- --n 10 --space-type sphere --p 2 ...
+
+``sys.path`` becomes ``[<dropin dir>, <reference dir>, ...]`` so ``import losses, encoders`` inside the script
+resolve to ``cl-ica_b200/dropin`` while every other module (spaces, latent_spaces, layers, ...) still comes
+from the reference checkout.  The script file itself is executed unmodified with ``runpy.run_path``.
+"""
+import argparse
+import os
+import runpy
+import sys
+import warnings
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--reference", default=os.environ.get("CLICA_REFERENCE_DIR", "/root/reference"))
+    ap.add_argument("--script", default="main_mlp.py")
+    ap.add_argument("script_args", nargs=argparse.REMAINDER)
+    args = ap.parse_args(argv)
+    ref = os.path.abspath(args.reference)
+    script = os.path.join(ref, args.script)
+    if not os.path.isfile(script):
+        raise SystemExit(f"{script} not found (pass --reference)")
+    import clica_b200
+    os.environ["CLICA_REFERENCE_DIR"] = ref
+    sys.path[:] = [clica_b200.DROPIN_DIR, ref] + [p for p in sys.path if p not in (clica_b200.DROPIN_DIR, ref)]
+    rest = args.script_args
+    if rest and rest[0] == "--":
+        rest = rest[1:]
+    sys.argv = [script] + rest
+    warnings.simplefilter("ignore", SyntaxWarning)
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

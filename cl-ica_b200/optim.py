@@ -1,0 +1,42 @@
+"""FusedAdam: ``torch.optim.Optimizer``-compatible Adam on ``clica_adam_step`` (one launch per 32 tensors).
+
+Same update rule and defaults as ``torch.optim.Adam(params, lr)`` used by ``main_mlp.py:312`` (betas
+(0.9, 0.999), eps 1e-8, no weight decay, no amsgrad).  ``main_mlp.py`` itself keeps ``torch.optim.Adam``
+(the script runs unchanged); this class is what ``bench.py`` and the sharded step use.
+"""
+import torch
+
+from . import functional as F
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps, gs, ms, vs = [], [], [], []
+            step = None
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                step = st["step"] if step is None else step
+                if st["step"] != step:
+                    raise RuntimeError("FusedAdam: parameters of one group must share their step count")
+                ps.append(p.data), gs.append(p.grad.contiguous()), ms.append(st["exp_avg"]), vs.append(st["exp_avg_sq"])
+            if ps:
+                F.adam_step(ps, gs, ms, vs, group["lr"], group["betas"][0], group["betas"][1], group["eps"], step)
+        return loss

@@ -1,0 +1,148 @@
+"""Row-sharded InfoNCE step: one process per GPU, NCCL over NVLink.
+
+The reference is single-device (``main_mlp.py:14-18``); its only multi-GPU construct gathers encoder
+outputs and evaluates the loss over the full batch (``main_3dident.py:373,480-492``).  This module keeps
+exactly those semantics -- every anchor sees ALL negatives of the global batch -- while sharding the work:
+
+  rank r owns anchors/positives [r*B/W, (r+1)*B/W)
+  fwd : a_r = f(g(z1_r)), b_r = f(g(z2_r))          encoder on the local shard
+        z_all   = all_gather(a_r)                   (B_global x d, 0.25 .. 1.3 MB: latency-bound)
+        loss_i, lse, pos = lpnce_fwd(a_r, b_r, z_all)        local rows x all columns
+        lse_all = all_gather(lse)                   (B_global floats)
+        loss    = all_reduce(sum_i loss_i) / B_global
+  bwd : g_a, g_b = lpnce_bwd_sharded(...)           anchor-role + column-role + positive terms for the
+                                                    LOCAL rows, already scaled by 1/B_global: no
+                                                    reduce-scatter of a B x d gradient is needed
+        encoder backward on the local shard, then ONE all_reduce(SUM) over the flattened parameter grads.
+
+The kernels are reached through ``ops`` (default: the CUDA C-ABI); tests inject an oracle-backed ``ops`` to
+exercise this host logic on CPU with the gloo backend.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+# ---- kernel access (CUDA) ---------------------------------------------------------------------------------
+def local_forward(z1_local, z2_local, z_all, p, tau, alpha, include_pos) -> Tuple[torch.Tensor, ...]:
+    """(loss_i, lse, pos) of the local anchors against all gathered rows (clica_lpnce_fwd)."""
+    from . import functional as F
+    lib = _lib.load()
+    z1, z2, za = F._as_rows(z1_local, "z1_local"), F._as_rows(z2_local, "z2_local"), F._as_rows(z_all, "z_all")
+    B, d = z1.shape
+    M = za.shape[0]
+    dev = z1.device
+    with torch.cuda.device(dev):
+        out = torch.empty(3 * B + 3, dtype=torch.float32, device=dev)
+        ws = F._workspace(lib.clica_lpnce_workspace_bytes(B, M, d), dev, "lpnce")
+        rc = lib.clica_lpnce_fwd(z1.data_ptr(), F._ld(z1), z2.data_ptr(), F._ld(z2), za.data_ptr(), F._ld(za),
+                                 B, M, d, float(p), float(tau), float(alpha), int(include_pos), 1,
+                                 out.data_ptr(), out[B:].data_ptr(), out[2 * B:].data_ptr(), out[3 * B:].data_ptr(),
+                                 ws.data_ptr(), ws.numel(), F._stream_ptr(dev))
+        _lib.check(rc, "clica_lpnce_fwd")
+    return out[:B], out[B:2 * B], out[2 * B:3 * B]
+
+
+def local_backward(z1_local, z2_local, z_all, lse_all, pos_local, row0, p, tau, alpha, include_pos,
+                   g_scale: Optional[torch.Tensor] = None):
+    """Gradient of the GLOBAL mean loss w.r.t. the local anchors / positives (clica_lpnce_bwd_sharded)."""
+    from . import functional as F
+    lib = _lib.load()
+    z1, z2, za = F._as_rows(z1_local, "z1_local"), F._as_rows(z2_local, "z2_local"), F._as_rows(z_all, "z_all")
+    B, d = z1.shape
+    M = za.shape[0]
+    dev = z1.device
+    lse_all = lse_all.contiguous()
+    pos_local = pos_local.contiguous()
+    with torch.cuda.device(dev):
+        g1 = torch.empty((B, d), dtype=torch.float32, device=dev)
+        g2 = torch.empty((B, d), dtype=torch.float32, device=dev)
+        if g_scale is not None:
+            g_scale = g_scale.to(device=dev, dtype=torch.float32).contiguous()
+        ws = F._workspace(lib.clica_lpnce_bwd_sharded_workspace_bytes(B, M, d), dev, "lpnce_bwd")
+        rc = lib.clica_lpnce_bwd_sharded(z1.data_ptr(), F._ld(z1), z2.data_ptr(), F._ld(z2), za.data_ptr(), F._ld(za),
+                                         lse_all.data_ptr(), pos_local.data_ptr(), B, M, d, int(row0), float(p),
+                                         float(tau), float(alpha), int(include_pos),
+                                         None if g_scale is None else g_scale.data_ptr(),
+                                         g1.data_ptr(), d, g2.data_ptr(), d, ws.data_ptr(), ws.numel(),
+                                         F._stream_ptr(dev))
+        _lib.check(rc, "clica_lpnce_bwd_sharded")
+    return g1, g2
+
+
+class CudaOps:
+    local_forward = staticmethod(local_forward)
+    local_backward = staticmethod(local_backward)
+
+
+# ---- collectives ------------------------------------------------------------------------------------------
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+class _ShardedInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a_local, b_local, p, tau, alpha, include_pos, group, ops):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        a_det, b_det = a_local.detach(), b_local.detach()
+        z_all = _all_gather_rows(a_det, group)
+        loss_i, lse, pos = ops.local_forward(a_det, b_det, z_all, p, tau, alpha, include_pos)
+        lse_all = _all_gather_rows(lse, group)
+        stats = torch.stack([loss_i.sum(), pos.sum() / tau, lse.sum()])
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+        stats = stats / z_all.shape[0]
+        ctx.save_for_backward(a_det, b_det, z_all, lse_all, pos)
+        ctx.cfg = (p, tau, alpha, include_pos, rank * a_local.shape[0], ops)
+        ctx.mark_non_differentiable(loss_i)
+        return stats[0], loss_i, stats[1:].detach()
+
+    @staticmethod
+    def backward(ctx, g_mean, _g_li, _g_parts):
+        a, b, z_all, lse_all, pos = ctx.saved_tensors
+        p, tau, alpha, include_pos, row0, ops = ctx.cfg
+        g1, g2 = ops.local_backward(a, b, z_all, lse_all, pos, row0, p, tau, alpha, include_pos, g_mean)
+        return g1, g2, None, None, None, None, None, None
+
+
+def sharded_lp_infonce(a_local, b_local, p, tau=1.0, alpha=0.5, include_pos=True, group=None, ops=CudaOps):
+    """Global-batch Lp-InfoNCE from local shards. Returns (global mean loss, local per-item loss,
+    tensor([global pos_mean, global neg_mean])).  Equal shard sizes on every rank are required."""
+    return _ShardedInfoNCE.apply(a_local, b_local, float(p), float(tau), float(alpha), bool(include_pos), group, ops)
+
+
+def allreduce_grads(params: List[torch.nn.Parameter], group=None) -> None:
+    """SUM the parameter gradients over ranks in one flattened bucket (NVLS in-switch reduce on NVSwitch).
+
+    The sharded loss already scales local gradients by 1/B_global, so the sum -- not the mean -- equals the
+    single-device full-batch gradient."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def sharded_train_step(f, g, optimizer, z1_local, z2_local, p, tau=1.0, alpha=0.5, group=None, ops=CudaOps):
+    """The body of ``main_mlp.py:258-285`` (unsupervised branch) on one rank's shard of the global batch.
+
+    Returns (global mean loss tensor, tensor([pos_mean, neg_mean])) -- 0-dim / 2-element device tensors; the
+    caller decides when to ``.item()`` them."""
+    optimizer.zero_grad()
+    a = f(g(z1_local))
+    b = f(g(z2_local))
+    loss, _, parts = sharded_lp_infonce(a, b, p, tau, alpha, True, group, ops)
+    loss.backward()
+    allreduce_grads([prm for prm in f.parameters()], group)
+    optimizer.step()
+    return loss.detach(), parts

@@ -1,0 +1,187 @@
+/*
+ * clica.h -- C ABI of libclica_sm100.so: the B200 (sm_100a) implementation of cl-ica's InfoNCE
+ * training-step hot path.  Plain C: device pointers, sizes, a cudaStream_t passed as void*.  No torch
+ * types, no C++ types, nothing thrown across the boundary.
+ *
+ * The reference (brendel-group/cl-ica) is pure Python on PyTorch and has no FFI of its own; each entry
+ * point below names the reference code (file:line under the reference root) whose arithmetic it replaces.
+ * The reference-side binding (ctypes stub + autograd.Function) is shown in INTEGRATION.md and shipped
+ * in cl-ica_b200/_lib.py / functional.py.
+ *
+ * Conventions
+ *   - all matrices are fp32, row-major, unit column stride, explicit leading dimension (in elements);
+ *   - every pointer is a DEVICE pointer into caller-owned memory (PyTorch caching allocator) unless
+ *     stated otherwise; the library allocates no persistent device memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never synchronises, never touches the
+ *     default stream, and is CUDA-graph capturable;
+ *   - return value: 0 on success; >0 a cudaError_t; <0 a CLICA_E_* code.  clica_last_error() returns a
+ *     thread-local description of the last failure on the calling thread.  No silent fallbacks.
+ */
+#ifndef CLICA_H_
+#define CLICA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLICA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CLICA_API __attribute__((visibility("default")))
+#else
+#define CLICA_API
+#endif
+
+#define CLICA_E_BADARG      (-1)  /* null pointer, negative size, ld < cols, ...              */
+#define CLICA_E_UNSUPPORTED (-2)  /* combination not implemented by the CUDA path (e.g. p < 1) */
+#define CLICA_E_WORKSPACE   (-3)  /* workspace too small                                       */
+#define CLICA_E_ALIGN       (-4)  /* pointer/ld alignment requirement violated                 */
+#define CLICA_E_ARCH        (-5)  /* device is not compute capability 10.x                     */
+
+/* GEMM numeric modes of the encoder kernels */
+#define CLICA_GEMM_3XTF32 0       /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: ~fp32 accuracy (parity mode) */
+#define CLICA_GEMM_TF32   1       /* tcgen05 kind::tf32 single pass (fast mode, ~1e-3 relative)            */
+#define CLICA_GEMM_FP32   3       /* CUDA-core FFMA, exact fp32 products (skinny layers; debug)            */
+
+CLICA_API int         clica_abi_version(void);
+CLICA_API const char* clica_last_error(void);
+/* Fills sm_count / cc_major / cc_minor of the current device; any pointer may be NULL. */
+CLICA_API int         clica_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lp-InfoNCE loss, forward.         replaces  losses.py:443-477 (LpSimCLRLoss.loss, p >= 1 branch)
+ *                                             losses.py:506-510 (_logmeanexp)
+ *
+ *   D_ik  = sum_c |z1[i,c] - z3[k,c]|^p ,  pos_i = sum_c |z1[i,c] - z2[i,c]|^p      (i < B, k < M)
+ *   include_pos = 1 (simclr_compatibility_mode):  lse_i = log( sum_k e^{-D_ik/tau} + e^{-pos_i/tau} )
+ *   include_pos = 0:                              lse_i = log( sum_k e^{-D_ik/tau} ) - log M
+ *   loss_i = 2 ( alpha pos_i / tau + (1 - alpha) lse_i )
+ *
+ * The B x M distance matrix is never materialised: anchors stay in registers, negatives stream through
+ * shared memory, the row soft-max is evaluated online.
+ *
+ * outputs  loss_i[B], lse[B] (as defined above), pos[B] (un-scaled pos_i),
+ *          scalars[3] = { mean_i loss_i, mean_i pos_i/tau, mean_i lse_i }   (losses.py:469-477)
+ * p        any real >= 1; p in {1,2,3,4} use multiply-only inner loops, other p use ex2/lg2.
+ * use_pow  must be 1 (losses.py:452-454, `pow=True`, the only value any reference script uses).
+ * ws       scratch of at least clica_lpnce_workspace_bytes(B, M, d) bytes, 16-byte aligned; its
+ *          contents after the forward (un-shifted log2-domain lse) are consumed by the backward.
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API size_t clica_lpnce_workspace_bytes(int B, int M, int d);
+
+CLICA_API int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
+                    int B, int M, int d, float p, float tau, float alpha, int include_pos,
+                    int use_pow, float* loss_i, float* lse, float* pos, float* scalars3,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lp-InfoNCE loss, backward.        replaces  autograd through losses.py:447-477
+ *                                   (LogsumexpBackward, CatBackward, PowBackward,
+ *                                    LinalgVectorNormBackward, SubBackward)
+ *
+ * Gradient of  L = g_mean * mean_i loss_i + sum_i g_loss_i[i] * loss_i  with respect to z1, z2, z3.
+ *   g_mean    device scalar (nullable => 0):  dL/d scalars3[0]
+ *   g_loss_i  device [B]    (nullable => 0):  dL/d loss_i
+ *   lse, pos  the forward's outputs
+ *   g_z1[B,d] (ld = ldg1), g_z2[B,d], g_z3[M,d]: any may be NULL (skipped).  g_z1 receives only the
+ *             anchor-role term; a caller whose z3 aliases z1 (torch.roll, main_mlp.py:272) adds g_z3
+ *             back through its own autograd graph exactly as the reference does.
+ * Zero differences contribute exactly zero (torch's norm backward masks them).
+ * ws: >= clica_lpnce_bwd_workspace_bytes(B, M, d) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API size_t clica_lpnce_bwd_workspace_bytes(int B, int M, int d);
+
+CLICA_API int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
+                    int B, int M, int d, float p, float tau, float alpha, int include_pos,
+                    int use_pow, const float* lse, const float* pos, const float* g_mean,
+                    const float* g_loss_i, float* g_z1, int ldg1, float* g_z2, int ldg2,
+                    float* g_z3, int ldg3, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-sharded variant (one process per GPU).  The caller all-gathers the encoder
+ * outputs (NCCL) so that z_all[M,d] holds every rank's anchors, runs clica_lpnce_fwd on its own rows
+ * [row0, row0+B) against z_all, all-gathers lse into lse_all[M], then calls this: it returns, for the
+ * LOCAL rows only, the complete gradient of the GLOBAL mean loss  (1/M) sum_i loss_i  with
+ * z3 = roll(z_all, 1):   anchor-role term + column-role term (rows i of every rank that use local
+ * row k as a negative, weights exp(-D_ik/tau - lse_all[i])) + positive term.  No second collective.
+ *   g_scale  device scalar: dL/d(global mean loss)   (nullable => 1)
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API size_t clica_lpnce_bwd_sharded_workspace_bytes(int B, int M, int d);
+
+CLICA_API int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const float* z2_local, int ld2,
+                            const float* z_all, int ld3, const float* lse_all,
+                            const float* pos_local, int B, int M, int d, int row0, float p,
+                            float tau, float alpha, int include_pos, const float* g_scale,
+                            float* g_z1, int ldg1, float* g_z2, int ldg2,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder layer kernels.            replace  nn.Linear + nn.LeakyReLU of encoders.py:38-48
+ *                                   (ATen addmm / leaky_relu and their autograd: AddmmBackward,
+ *                                    LeakyReluBackward)
+ *
+ *   fwd        y[M,N]  = act( x[M,K] W[N,K]^T + b[N] ),  act = LeakyReLU(slope) or identity (slope = 1)
+ *   bwd_data   dx[M,K] = ( dy[M,N] W[N,K] ) * act'(x_act) ,  act'(v) = v > 0 ? 1 : slope_prev
+ *              (x_act = this layer's INPUT = previous layer's activation output; nullable => no mask)
+ *   bwd_weight dW[N,K] = dy[M,N]^T x[M,K] ,  db[N] = sum_m dy[m,:]         (db nullable)
+ *
+ * `mode` is one of CLICA_GEMM_*.  Tensor-core modes stage fp32 operands with TMA into 128B-swizzled
+ * shared memory and accumulate in TMEM (tcgen05.mma kind::tf32); shapes the tensor-core path cannot
+ * address (leading dimension not a multiple of 4 floats, K or N < 16) are routed to the exact-fp32
+ * CUDA-core kernel inside the same call -- that is a shape rule documented in DESIGN.md, not a fallback.
+ * ws: >= clica_linear_workspace_bytes(M, N, K, mode) bytes, 1024-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API size_t clica_linear_workspace_bytes(int M, int N, int K, int mode);
+
+CLICA_API int clica_linear_act_fwd(const float* x, int ldx, const float* W, int ldw, const float* b,
+                         float* y, int ldy, int M, int K, int N, float slope, int mode,
+                         void* ws, size_t ws_bytes, void* stream);
+
+CLICA_API int clica_linear_act_bwd_data(const float* dy, int lddy, const float* W, int ldw,
+                              const float* x_act, int ldxa, float slope_prev,
+                              float* dx, int lddx, int M, int K, int N, int mode,
+                              void* ws, size_t ws_bytes, void* stream);
+
+CLICA_API int clica_linear_bwd_weight(const float* dy, int lddy, const float* x, int ldx,
+                            float* dW, int lddw, float* db, int M, int K, int N, int mode,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-encoder calls (one C call per forward / backward of the Linear+LeakyReLU stack, so the host
+ * pays one FFI crossing instead of 7 / 20).            replaces  encoders.py:36-58 forward + autograd
+ *
+ * Layer l (0 <= l < L): W[l] is [widths[l+1], widths[l]] (ld = widths[l]), b[l] is [widths[l+1]].
+ * acts[l] (l = 0..L) are caller-allocated [M, widths[l]] dense buffers: acts[0] = input x,
+ * acts[L] = output; the hidden ones are what the backward needs (saved by the caller's autograd ctx).
+ * LeakyReLU(slope) after every layer but the last.
+ * backward: g_out = dL/d acts[L]; dW[l], db[l] are written (not accumulated); g_in nullable
+ * (main_mlp.py feeds the frozen mixing net's output, which needs no gradient).
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode);
+
+CLICA_API int clica_mlp_fwd(int L, const int* widths, const float* const* W, const float* const* b,
+                  float* const* acts, int M, float slope, int mode,
+                  void* ws, size_t ws_bytes, void* stream);
+
+CLICA_API int clica_mlp_bwd(int L, const int* widths, const float* const* W, const float* const* acts,
+                  const float* g_out, float* const* dW, float* const* db, float* g_in,
+                  int M, float slope, int mode, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam step.     replaces  torch.optim.Adam.step (main_mlp.py:283,312) for the
+ *                                   encoder's parameter list; same update rule as torch's default
+ *                                   (no amsgrad, no weight decay, eps added after the bias-corrected
+ *                                   sqrt).  Host arrays of `n` device pointers / element counts.
+ *   step is the 1-based step count AFTER this update.
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API int clica_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1,
+                    float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLICA_H_ */

@@ -1,0 +1,106 @@
+"""GPU (-m gpu): encoder kernels through the C ABI vs the numpy fp64 oracle and the reference golden vectors.
+
+Tolerances: CLICA_GEMM_FP32 (exact fp32 products) and CLICA_GEMM_3XTF32 (hi/lo split, ~2^-21 per product)
+are both held to 2e-5 relative to the tensor's max magnitude -- the band the reference's own fp32 cuBLAS
+path occupies (2e-6..1e-5).  CLICA_GEMM_TF32 is the labelled fast mode: 5e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"fp32": (3, 2e-5), "3xtf32": (0, 2e-5), "tf32": (1, 5e-3)}
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("mode_name", list(MODES))
+def test_golden_small_mlp(mode_name, cuda_device):
+    from clica_b200 import functional as F
+    mode, tol = MODES[mode_name]
+    g = load_golden("mlp_small")
+    keys = [str(k) for k in g["keys"]]
+    wk = [k for k in keys if k.endswith("weight")]
+    bk = [k for k in keys if k.endswith("bias")]
+    Ws = [torch.tensor(g["param_" + k], device=cuda_device, requires_grad=True) for k in wk]
+    bs = [torch.tensor(g["param_" + k], device=cuda_device, requires_grad=True) for k in bk]
+    x = torch.tensor(g["x"], device=cuda_device, requires_grad=True)
+    y = F.mlp_forward(x, Ws, bs, slope=0.01, mode=mode)
+    y.backward(torch.tensor(g["gy"], device=cuda_device))
+    assert _rel(y.detach().cpu().numpy(), g["y_64"]) <= tol
+    assert _rel(x.grad.cpu().numpy(), g["dx_64"]) <= tol
+    for k, W in zip(wk, Ws):
+        assert _rel(W.grad.cpu().numpy(), g["grad64_" + k]) <= tol, k
+    for k, b in zip(bk, bs):
+        assert _rel(b.grad.cpu().numpy(), g["grad64_" + k]) <= tol, k
+
+
+@pytest.mark.parametrize("mode_name", list(MODES))
+@pytest.mark.parametrize("n,M", [(5, 200), (10, 1000), (16, 333)])
+def test_encoder_stack_against_numpy_oracle(mode_name, n, M, cuda_device):
+    """The real encoder shape n -> 10n -> 50n x4 -> 10n -> n (main_mlp.py:297-309), ragged M."""
+    from clica_b200 import functional as F
+    from oracle import mlp_oracle
+    mode, tol = MODES[mode_name]
+    rng = np.random.RandomState(n + M)
+    widths = [n, 10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n, n]
+    Wn = [(rng.uniform(-1, 1, size=(widths[i + 1], widths[i])) / np.sqrt(widths[i])).astype(np.float32) for i in range(7)]
+    bn = [(rng.uniform(-1, 1, size=(widths[i + 1],)) / np.sqrt(widths[i])).astype(np.float32) for i in range(7)]
+    xn = rng.randn(M, n).astype(np.float32)
+    gyn = rng.randn(M, n).astype(np.float32)
+    Ws = [torch.tensor(w, device=cuda_device, requires_grad=True) for w in Wn]
+    bs = [torch.tensor(b, device=cuda_device, requires_grad=True) for b in bn]
+    x = torch.tensor(xn, device=cuda_device, requires_grad=True)
+    y = F.mlp_forward(x, Ws, bs, slope=0.01, mode=mode)
+    y.backward(torch.tensor(gyn, device=cuda_device))
+    y_ref, acts, pre = mlp_oracle.mlp_forward(xn, Wn, bn, slope=0.01)
+    dWs, dbs, dx = mlp_oracle.mlp_backward(gyn, Wn, acts, pre, slope=0.01, need_dx=True)
+    assert _rel(y.detach().cpu().numpy(), y_ref) <= tol
+    assert _rel(x.grad.cpu().numpy(), dx) <= tol
+    for l in range(7):
+        assert _rel(Ws[l].grad.cpu().numpy(), dWs[l]) <= tol, f"dW{l}"
+        assert _rel(bs[l].grad.cpu().numpy(), dbs[l]) <= tol, f"db{l}"
+
+
+def test_dropin_get_mlp_on_cuda_matches_torch_modules(cuda_device):
+    """The FusedMLP returned by the drop-in get_mlp must agree with the same nn modules run by torch."""
+    import sys
+    import clica_b200
+    sys.path.insert(0, clica_b200.DROPIN_DIR)
+    import encoders
+    torch.manual_seed(5)
+    n = 10
+    f = encoders.get_mlp(n, n, [10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n]).to(cuda_device)
+    x = torch.randn(777, n, device=cuda_device)
+    y = f(x)
+    y_t = torch.nn.Sequential.forward(f, x)          # plain torch execution of the very same modules (fp32 cuBLAS)
+    assert (y - y_t).abs().max().item() <= 2e-5 * y_t.abs().max().item()
+    (y ** 2).mean().backward()
+    g_fused = [p.grad.clone() for p in f.parameters()]
+    f.zero_grad()
+    (y_t ** 2).mean().backward()
+    for gf, p in zip(g_fused, f.parameters()):
+        assert (gf - p.grad).abs().max().item() <= 5e-5 * (p.grad.abs().max().item() + 1e-30)
+    assert list(f.state_dict().keys())[:2] == ["0.weight", "0.bias"]
+
+
+def test_fused_adam_matches_torch_adam(cuda_device):
+    from clica_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(100, 10), (100,), (500, 100), (500,), (7,), (1, 1)]
+    p_ref = [torch.randn(s, device=cuda_device, requires_grad=True) for s in shapes]
+    p_fus = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    o_ref = torch.optim.Adam(p_ref, lr=1e-3)
+    o_fus = FusedAdam(p_fus, lr=1e-3)
+    for _ in range(5):
+        for a, b in zip(p_ref, p_fus):
+            g = torch.randn_like(a)
+            a.grad, b.grad = g.clone(), g.clone()
+        o_ref.step(), o_fus.step()
+    for a, b in zip(p_ref, p_fus):
+        assert (a - b).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
