@@ -82,7 +82,7 @@ extern "C" int clica_adam_step(int n, float* const* params, const float* const* 
         a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
         a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
         if (chunks == 0) continue;
-        adam_kernel<<<chunks, 256, 0, st>>>(a);
+        { LaunchScope ls(st, kFamAdam); adam_kernel<<<chunks, 256, 0, st>>>(a); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     return 0;

@@ -41,6 +41,26 @@ struct DeviceInfo {
 };
 int get_device_info(DeviceInfo* out);   // cached per device; defined in abi.cu
 
+// ---- launch accounting / optional per-family CUDA-event timing (bench.py's roofline numbers) ------
+enum KernelFamily : int {
+    kFamLossFwd = 0,    // lpnce_fwd_kernel
+    kFamLossBwd = 1,    // lpnce_bwd_kernel
+    kFamLossAux = 2,    // finalize / prep / reduce
+    kFamGemmTc = 3,     // tcgen05 GEMM
+    kFamGemmSimt = 4,   // CUDA-core GEMM
+    kFamAdam = 5,
+    kFamMisc = 6,       // column sums, operand packing
+    kNumFamilies = 7
+};
+// RAII: counts `launches` kernels for `family`; when profiling is enabled also brackets them with a pair of
+// CUDA events on `st` (read back by clica_prof_collect).  Defined in abi.cu.
+struct LaunchScope {
+    LaunchScope(cudaStream_t st, int family, int launches = 1);
+    ~LaunchScope();
+    cudaStream_t st_;
+    int slot_;
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -20,7 +20,7 @@ int simt_linear_fwd(const float* x, int ldx, const float* W, int ldw, const floa
     q.C = y; q.ldc = ldy; q.M = M; q.N = N; q.K = K; q.k_chunk = K;
     q.bias = b; q.aux = nullptr; q.ldaux = 0; q.slope = slope; q.epilogue = kEpiBiasAct;
     dim3 grid(ceil_div(N, kSBN), ceil_div(M, kSBM), 1);
-    gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(q);
+    { LaunchScope ls(st, kFamGemmSimt); gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(q); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -33,7 +33,7 @@ int simt_linear_bwd_data(const float* dy, int lddy, const float* W, int ldw, con
     q.C = dx; q.ldc = lddx; q.M = M; q.N = K; q.K = N; q.k_chunk = N;
     q.bias = nullptr; q.aux = x_act; q.ldaux = ldxa; q.slope = slope_prev; q.epilogue = kEpiMask;
     dim3 grid(ceil_div(K, kSBN), ceil_div(M, kSBM), 1);
-    gemm_simt_kernel<true, false><<<grid, 256, 0, st>>>(q);
+    { LaunchScope ls(st, kFamGemmSimt); gemm_simt_kernel<true, false><<<grid, 256, 0, st>>>(q); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -55,10 +55,10 @@ int simt_linear_bwd_weight(const float* dy, int lddy, const float* x, int ldx, f
     q.C = dW; q.ldc = lddw; q.M = N; q.N = K; q.K = M; q.k_chunk = chunk;
     q.bias = nullptr; q.aux = nullptr; q.ldaux = 0; q.slope = 1.f; q.epilogue = kEpiAtomic;
     dim3 grid(ceil_div(K, kSBN), ceil_div(N, kSBM), splits);
-    gemm_simt_kernel<false, false><<<grid, 256, 0, st>>>(q);
+    { LaunchScope ls(st, kFamGemmSimt); gemm_simt_kernel<false, false><<<grid, 256, 0, st>>>(q); }
     CLICA_CUDA_OK(cudaGetLastError());
     if (db) {
-        colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, st>>>(dy, lddy, M, N, db);
+        { LaunchScope ls(st, kFamMisc); colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, st>>>(dy, lddy, M, N, db); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     return 0;

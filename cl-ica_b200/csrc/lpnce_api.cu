@@ -286,7 +286,7 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
     q.coef = kLog2e / tau; q.pg = p;
     q.tiles_per_split = pl.tiles_per_split; q.flat16 = is_flat16(z3, ld3, d, DP);
     q.part_m = w.part_m; q.part_s = w.part_s; q.part_stride = B; q.counter = w.counter;
-    rc = dispatch_fwd(p_code(p), DP, q, dim3(pl.row_tiles, pl.nsplit, 1), st);
+    { LaunchScope ls(st, kFamLossFwd); rc = dispatch_fwd(p_code(p), DP, q, dim3(pl.row_tiles, pl.nsplit, 1), st); }
     if (rc) return rc;
 
     FinParams f;
@@ -295,7 +295,7 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
     f.alpha = alpha; f.include_pos = include_pos;
     f.loss_i = loss_i; f.lse = lse; f.pos = pos; f.scalars = scalars3;
     f.block_sums = w.block_sums; f.counter = w.counter;
-    lpnce_finalize_kernel<<<ceil_div(B, 256), 256, 0, st>>>(f);
+    { LaunchScope ls(st, kFamLossAux); lpnce_finalize_kernel<<<ceil_div(B, 256), 256, 0, st>>>(f); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -332,7 +332,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
     pp.inv_count = 1.f / (float)B; pp.shift = include_pos ? 0.f : logf((float)M);
     pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
     pp.L2 = w.L2; pp.E = w.E; pp.CP = w.CP; pp.default_g = 0.f;
-    lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp);
+    { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
 
     const bool needA = (g_z1 != nullptr), needB = (g_z3 != nullptr);
@@ -356,7 +356,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
             r.part = w.partB; r.part_rows = M; r.row_tiles = pb.row_tiles;
             gx = max(gx, pb.row_tiles); gy = max(gy, pb.nsplit);
         }
-        rc = dispatch_bwd(p_code(p), DP, q, dim3(gx, gy, q.nroles), st);
+        { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(gx, gy, q.nroles), st); }
         if (rc) return rc;
     }
     if (g_z1 || g_z2) {
@@ -367,7 +367,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
         r.rows = B; r.d = d; r.TW = TW; r.p = p;
         const long long n = (long long)B * d;
-        lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r);
+        { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     if (g_z3) {
@@ -378,7 +378,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         r.g_out = g_z3; r.ldg = ldg3; r.g_z2 = nullptr; r.ldg2 = 0;
         r.rows = M; r.d = d; r.TW = TW; r.p = p;
         const long long n = (long long)M * d;
-        lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r);
+        { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -419,11 +419,11 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     pp.inv_count = 1.f / (float)M; pp.shift = include_pos ? 0.f : logf((float)M);
     pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
     pp.L2 = w.L2; pp.E = w.E; pp.CP = nullptr; pp.default_g = 1.f;
-    lpnce_prep_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pp);
+    { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
     // ... and the positive-pair coefficient of the local rows
     pp.lse = lse_all + row0; pp.pos = pos_local; pp.n = B; pp.L2 = nullptr; pp.E = nullptr; pp.CP = w.CP;
-    lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp);
+    { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
 
     BwdParams q;
@@ -437,7 +437,7 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     }
     q.role[0].LO = w.L2 + row0; q.role[0].LS = nullptr; q.role[0].ES = nullptr; q.role[0].part = w.partA;   // local rows as anchors
     q.role[1].LO = nullptr; q.role[1].LS = w.L2; q.role[1].ES = w.E; q.role[1].part = w.partB;             // local rows as negatives
-    rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 2), st);
+    { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 2), st); }
     if (rc) return rc;
 
     ReduceParams r;
@@ -447,7 +447,7 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
     r.rows = B; r.d = d; r.TW = TW; r.p = p;
     const long long n = (long long)B * d;
-    lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r);
+    { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }

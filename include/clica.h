@@ -67,8 +67,8 @@ CLICA_API int         clica_device_info(int* sm_count, int* cc_major, int* cc_mi
  *          scalars[3] = { mean_i loss_i, mean_i pos_i/tau, mean_i lse_i }   (losses.py:469-477)
  * p        any real >= 1; p in {1,2,3,4} use multiply-only inner loops, other p use ex2/lg2.
  * use_pow  must be 1 (losses.py:452-454, `pow=True`, the only value any reference script uses).
- * ws       scratch of at least clica_lpnce_workspace_bytes(B, M, d) bytes, 16-byte aligned; its
- *          contents after the forward (un-shifted log2-domain lse) are consumed by the backward.
+ * ws       scratch of at least clica_lpnce_workspace_bytes(B, M, d) bytes, 16-byte aligned (split
+ *          partials; dead after the call -- the backward is stateless and takes lse / pos back).
  * ---------------------------------------------------------------------------------------------- */
 CLICA_API size_t clica_lpnce_workspace_bytes(int B, int M, int d);
 
@@ -180,6 +180,20 @@ CLICA_API int clica_mlp_bwd(int L, const int* widths, const float* const* W, con
 CLICA_API int clica_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
                     float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1,
                     float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Launch accounting (bench.py's `gpu_launches` and per-kernel roofline numbers; no reference analogue).
+ *   clica_launch_count(family)  kernels launched by this library in this process (family < 0: all)
+ *   clica_prof_enable(on)       when on, every launch scope is bracketed by CUDA events on its stream
+ *   clica_prof_collect(ms, n)   host arrays of CLICA_NUM_FAMILIES entries: summed device time (ms) and
+ *                               number of scopes per kernel family since the last collect; synchronises.
+ * Families: 0 loss fwd, 1 loss bwd, 2 loss finalize/prep/reduce, 3 tcgen05 GEMM, 4 CUDA-core GEMM,
+ *           5 Adam, 6 misc (column sums, operand packing).
+ * ---------------------------------------------------------------------------------------------- */
+#define CLICA_NUM_FAMILIES 7
+CLICA_API long long clica_launch_count(int family);
+CLICA_API int clica_prof_enable(int on);
+CLICA_API int clica_prof_collect(float* ms_by_family, int* scopes_by_family);
 
 #ifdef __cplusplus
 }
