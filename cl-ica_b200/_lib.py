@@ -27,7 +27,7 @@ SIGNATURES = {
     "clica_device_info": (_c_int, [_vp, _vp, _vp]),
     "clica_lpnce_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "clica_lpnce_fwd": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_float,
-                                 _c_float, _c_float, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_size_t, _vp]),
+                                 _c_float, _c_float, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _c_size_t, _vp]),
     "clica_lpnce_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "clica_lpnce_bwd": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_float,
                                  _c_float, _c_float, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp,
@@ -43,6 +43,7 @@ SIGNATURES = {
                                            _c_int, _c_int, _c_int, _c_int, _vp, _c_size_t, _vp]),
     "clica_linear_bwd_weight": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _c_int,
                                          _c_int, _vp, _c_size_t, _vp]),
+    "clica_mlp_act_floats": (_c_size_t, [_c_int, _c_int, _c_int]),
     "clica_mlp_workspace_bytes": (_c_size_t, [_c_int, _c_int, _vp, _c_int]),
     "clica_mlp_fwd": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _c_int, _c_float, _c_int, _vp, _c_size_t, _vp]),
     "clica_mlp_bwd": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_float, _c_int, _vp,

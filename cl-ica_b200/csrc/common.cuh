@@ -91,6 +91,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// nearest-even rounding of an fp32 value to tf32 precision (10 explicit mantissa bits); the result is exactly
+// representable in tf32, so the tensor core's own fp32 -> tf32 conversion cannot change it.
+__device__ __forceinline__ float round_to_tf32(float v) {
+    uint32_t u = __float_as_uint(v);
+    u += 0xFFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,6 +6,8 @@
 // 128x128x8 tiles, 256 threads, 8x8 outputs per thread (two 4-wide groups 64 apart so that the 128-bit
 // shared-memory reads are conflict-free), register-staged double buffering.  A_KC / B_KC say whether the
 // operand is contiguous along the reduction dimension (selects the coalesced global-load mapping).
+// Operands / results may be (hi, lo) plane pairs of the tensor-core path (value = hi + lo): the layers next
+// to a tcgen05 layer read and write that format directly.
 #pragma once
 #include "common.cuh"
 
@@ -18,9 +20,9 @@ enum SimtEpilogue : int {
 };
 
 struct SimtGemmParams {
-    const float* A; long long a_sm, a_sk;
-    const float* B; long long b_sk, b_sn;
-    float* C; int ldc;
+    const float* A; const float* A_lo; long long a_sm, a_sk;     // A_lo nullable (same strides)
+    const float* B; const float* B_lo; long long b_sk, b_sn;     // B_lo nullable
+    float* C; float* C_lo; int ldc;                              // C_lo non-null: C = tf32-round(v), C_lo = v - C
     int M, N, K;
     int k_chunk;             // reduction elements per blockIdx.z (split-K); == K when gridDim.z == 1
     const float* bias;       // [N] or null
@@ -56,9 +58,19 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtGemmParams 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = m0 + a_row[i], k = k0 + a_k[i];
-            ra[i] = (m < q.M && k < kend) ? __ldg(q.A + m * q.a_sm + k * q.a_sk) : 0.f;
+            float va = 0.f;
+            if (m < q.M && k < kend) {
+                va = __ldg(q.A + m * q.a_sm + k * q.a_sk);
+                if (q.A_lo) va += __ldg(q.A_lo + m * q.a_sm + k * q.a_sk);
+            }
+            ra[i] = va;
             const int n = n0 + b_col[i], kb = k0 + b_k[i];
-            rb[i] = (n < q.N && kb < kend) ? __ldg(q.B + kb * q.b_sk + n * q.b_sn) : 0.f;
+            float vb = 0.f;
+            if (n < q.N && kb < kend) {
+                vb = __ldg(q.B + kb * q.b_sk + n * q.b_sn);
+                if (q.B_lo) vb += __ldg(q.B_lo + kb * q.b_sk + n * q.b_sn);
+            }
+            rb[i] = vb;
         }
     };
     auto stash = [&](int buf) {
@@ -111,46 +123,54 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtGemmParams 
             const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
             if (n >= q.N) continue;
             float v = acc[i][j];
-            float* dst = q.C + (size_t)m * q.ldc + n;
+            const size_t o = (size_t)m * q.ldc + n;
+            if (q.epilogue == kEpiAtomic) {
+                atomicAdd(q.C + o, v);
+                continue;
+            }
             if (q.epilogue == kEpiBiasAct) {
                 if (q.bias) v += __ldg(q.bias + n);
-                *dst = v > 0.f ? v : v * q.slope;
-            } else if (q.epilogue == kEpiMask) {
-                if (q.aux) v *= (__ldg(q.aux + (size_t)m * q.ldaux + n) > 0.f) ? 1.f : q.slope;
-                *dst = v;
+                v = v > 0.f ? v : v * q.slope;
+            } else if (q.aux) {
+                v *= (__ldg(q.aux + (size_t)m * q.ldaux + n) > 0.f) ? 1.f : q.slope;
+            }
+            if (q.C_lo) {
+                const float h = round_to_tf32(v);
+                q.C[o] = h;
+                q.C_lo[o] = v - h;
             } else {
-                atomicAdd(dst, v);
+                q.C[o] = v;
             }
         }
     }
 }
 
-// db[n] = sum_m dy[m, n]; one warp-wide strip of 32 columns per block column, rows strided over blockDim.y
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int ld, int M, int N,
-                                                      float* __restrict__ db) {
+// db[n] += sum_m (hi[m, n] + lo[m, n]) over this block's row range; db pre-zeroed
+static __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int ld,
+                                                      int M, int N, int rows_per_block, float* __restrict__ db) {
     __shared__ float red[8][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
+    const int mbeg = blockIdx.y * rows_per_block, mend = min(M, mbeg + rows_per_block);
     float s = 0.f;
     if (n < N)
-        for (int m = threadIdx.y; m < M; m += 8) s += __ldg(dy + (size_t)m * ld + n);
+        for (int m = mbeg + threadIdx.y; m < mend; m += 8) {
+            s += __ldg(hi + (size_t)m * ld + n);
+            if (lo) s += __ldg(lo + (size_t)m * ld + n);
+        }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && n < N) {
         float t = 0.f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
-        db[n] = t;
+        atomicAdd(db + n, t);
     }
 }
 
 #endif  // __CUDACC__
 
-// host launchers (defined in linear_api.cu)
-int simt_linear_fwd(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
-                    int M, int K, int N, float slope, cudaStream_t st);
-int simt_linear_bwd_data(const float* dy, int lddy, const float* W, int ldw, const float* x_act, int ldxa,
-                         float slope_prev, float* dx, int lddx, int M, int K, int N, cudaStream_t st);
-int simt_linear_bwd_weight(const float* dy, int lddy, const float* x, int ldx, float* dW, int lddw, float* db,
-                           int M, int K, int N, int sm_count, cudaStream_t st);
+// host launchers (defined in linear_api.cu); operands given as (hi, lo) pairs with lo nullable
+int simt_gemm(const SimtGemmParams& q, bool a_kc, bool b_kc, int splits, cudaStream_t st);
+int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* db, cudaStream_t st);
 
 }  // namespace clica

@@ -1,8 +1,43 @@
 // gemm_tc.cuh -- interface of the tcgen05 (5th-gen tensor core) TF32 / 3xTF32 GEMM path (gemm_tc.cu).
+//
+// Operands are "planar": a matrix is one fp32 plane (TF32 mode: the hardware drops the low 13 mantissa bits)
+// or a (hi, lo) pair of planes with  value = hi + lo,  hi exactly representable in tf32 (3xTF32 mode:
+// D += A_hi B_hi + A_lo B_hi + A_hi B_lo  -- three tensor-core MMAs per product, ~2^-21 relative error).
 #pragma once
 #include "common.cuh"
 
 namespace clica {
+
+struct PlanesIn { const float* hi; const float* lo; int ld; };    // lo == nullptr: single plane
+struct PlanesOut { float* hi; float* lo; int ld; };               // hi == nullptr: not written
+
+enum TcEpilogue : int {
+    kTcBiasAct = 0,   // v = leaky(acc + bias[n], slope)
+    kTcMask = 1,      // v = acc * (aux[m,n] > 0 ? 1 : slope)      (aux nullable: no mask)
+    kTcAtomic = 2,    // atomicAdd(out[m,n], acc)                  (split-K; out pre-zeroed by the caller)
+};
+
+// D[Mo x No] = sum_{r < Kr} A(mo, r) * B(no, r)
+struct TcGemm {
+    PlanesIn A; int a_mn_major;   // 0: stored [Mo rows][Kr cols] (K-major); 1: stored [Kr rows][Mo cols] (MN-major)
+    PlanesIn B; int b_mn_major;   // 0: stored [No rows][Kr cols];           1: stored [Kr rows][No cols]
+    int Mo, No, Kr;
+    int epi;
+    const float* bias; float slope;
+    const float* aux; int ldaux;
+    float* out; int ldo;          // plain fp32 output (nullable unless epi == kTcAtomic)
+    PlanesOut outp;               // planar output (hi = round-to-tf32(v), lo = v - hi), nullable
+    int allow_split_k;            // epi == kTcAtomic only
+};
+
+int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st);
+
+// ld of a plane holding `cols` columns: rows must be 16-byte multiples for TMA
+inline int plane_ld(int cols) { return (cols + 3) / 4 * 4; }
+
+// split a plain matrix into (hi, lo) planes (lo == nullptr: plain copy with the plane's ld)
+int tc_split_planes(const float* src, int ld_src, int rows, int cols, float* hi, float* lo, int ld_dst,
+                    cudaStream_t st);
 
 // true when the tensor-core kernel handles an [M_out x N_out] GEMM with reduction length K_red
 bool tc_shape_ok(int M_out, int N_out, int K_red);

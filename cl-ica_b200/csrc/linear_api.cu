@@ -4,67 +4,81 @@
 //
 // Shape rule (not a fallback): a layer goes to the tcgen05 tensor-core GEMM (gemm_tc.cu) when the
 // requested mode is a tensor-core mode AND TMA can address all three matrices (leading dimensions
-// multiples of 4 floats, 16-byte aligned bases) AND both K and N are >= 16; otherwise -- the n -> 10n and
+// multiples of 4 floats, 16-byte aligned bases) AND M, K, N are all >= 32; otherwise -- the n -> 10n and
 // 10n -> n layers of the encoder, whose rows are 40 bytes at n = 10 -- it runs on the exact-fp32
-// CUDA-core kernel of gemm_simt.cuh.
+// CUDA-core kernel of gemm_simt.cuh.  In the whole-stack calls the first and last layer always take the
+// CUDA-core kernel (they are <2% of the flops) and every hidden activation lives in the tensor-core
+// operand format ((hi, lo) planes in 3xTF32 mode) so that no conversion pass is ever needed.
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 
 namespace clica {
 
-int simt_linear_fwd(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
-                    int M, int K, int N, float slope, cudaStream_t st) {
-    SimtGemmParams q;
-    q.A = x; q.a_sm = ldx; q.a_sk = 1;
-    q.B = W; q.b_sk = 1; q.b_sn = ldw;
-    q.C = y; q.ldc = ldy; q.M = M; q.N = N; q.K = K; q.k_chunk = K;
-    q.bias = b; q.aux = nullptr; q.ldaux = 0; q.slope = slope; q.epilogue = kEpiBiasAct;
-    dim3 grid(ceil_div(N, kSBN), ceil_div(M, kSBM), 1);
-    { LaunchScope ls(st, kFamGemmSimt); gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(q); }
+int simt_gemm(const SimtGemmParams& q, bool a_kc, bool b_kc, int splits, cudaStream_t st) {
+    dim3 grid(ceil_div(q.N, kSBN), ceil_div(q.M, kSBM), splits);
+    LaunchScope ls(st, kFamGemmSimt);
+    if (a_kc && b_kc) gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(q);
+    else if (a_kc && !b_kc) gemm_simt_kernel<true, false><<<grid, 256, 0, st>>>(q);
+    else if (!a_kc && b_kc) gemm_simt_kernel<false, true><<<grid, 256, 0, st>>>(q);
+    else gemm_simt_kernel<false, false><<<grid, 256, 0, st>>>(q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int simt_linear_bwd_data(const float* dy, int lddy, const float* W, int ldw, const float* x_act, int ldxa,
-                         float slope_prev, float* dx, int lddx, int M, int K, int N, cudaStream_t st) {
-    SimtGemmParams q;
-    q.A = dy; q.a_sm = lddy; q.a_sk = 1;          // [M x N], reduce over N
-    q.B = W; q.b_sk = ldw; q.b_sn = 1;            // B(n, k) = W[n][k]
-    q.C = dx; q.ldc = lddx; q.M = M; q.N = K; q.K = N; q.k_chunk = N;
-    q.bias = nullptr; q.aux = x_act; q.ldaux = ldxa; q.slope = slope_prev; q.epilogue = kEpiMask;
-    dim3 grid(ceil_div(K, kSBN), ceil_div(M, kSBM), 1);
-    { LaunchScope ls(st, kFamGemmSimt); gemm_simt_kernel<true, false><<<grid, 256, 0, st>>>(q); }
+int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* db, cudaStream_t st) {
+    CLICA_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+    int ysplit = ceil_div(M, 256);
+    if (ysplit > 64) ysplit = 64;
+    const int rows_per_block = ceil_div(M, ysplit);
+    LaunchScope ls(st, kFamMisc);
+    colsum_kernel<<<dim3(ceil_div(N, 32), ysplit), dim3(32, 8), 0, st>>>(hi, lo, ld, M, N, rows_per_block, db);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int simt_linear_bwd_weight(const float* dy, int lddy, const float* x, int ldx, float* dW, int lddw, float* db,
-                           int M, int K, int N, int sm_count, cudaStream_t st) {
-    // dW[N x K] = dy^T x, reduction over the M rows: split-K so that the grid fills the SMs
+namespace {
+
+// y = act(x W^T + b); x, y given as (hi, lo) pairs (lo nullable)
+int simt_fwd(PlanesIn x, const float* W, int ldw, const float* b, PlanesOut y, int M, int K, int N, float slope,
+             cudaStream_t st) {
+    SimtGemmParams q = {};
+    q.A = x.hi; q.A_lo = x.lo; q.a_sm = x.ld; q.a_sk = 1;
+    q.B = W; q.B_lo = nullptr; q.b_sk = 1; q.b_sn = ldw;
+    q.C = y.hi; q.C_lo = y.lo; q.ldc = y.ld; q.M = M; q.N = N; q.K = K; q.k_chunk = K;
+    q.bias = b; q.slope = slope; q.epilogue = kEpiBiasAct;
+    return simt_gemm(q, true, true, 1, st);
+}
+// dx = (dy W) * mask(aux)
+int simt_bwd_data(PlanesIn dy, const float* W, int ldw, const float* aux, int ldaux, float slope_prev, PlanesOut dx,
+                  int M, int K, int N, cudaStream_t st) {
+    SimtGemmParams q = {};
+    q.A = dy.hi; q.A_lo = dy.lo; q.a_sm = dy.ld; q.a_sk = 1;      // [M x N], reduce over N
+    q.B = W; q.B_lo = nullptr; q.b_sk = ldw; q.b_sn = 1;          // B(n, k) = W[n][k]
+    q.C = dx.hi; q.C_lo = dx.lo; q.ldc = dx.ld; q.M = M; q.N = K; q.K = N; q.k_chunk = N;
+    q.aux = aux; q.ldaux = ldaux; q.slope = slope_prev; q.epilogue = kEpiMask;
+    return simt_gemm(q, true, false, 1, st);
+}
+// dW = dy^T x (split-K over the M rows, atomics into the zeroed dW), db = column sums of dy
+int simt_bwd_weight(PlanesIn dy, PlanesIn x, float* dW, int lddw, float* db, int M, int K, int N, int sm_count,
+                    cudaStream_t st) {
     const int tiles = ceil_div(N, kSBM) * ceil_div(K, kSBN);
     int splits = (2 * sm_count + tiles - 1) / tiles;
     const int max_splits = ceil_div(M, 4 * kSBK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    int chunk = ceil_div(ceil_div(M, splits), kSBK) * kSBK;
+    const int chunk = ceil_div(ceil_div(M, splits), kSBK) * kSBK;
     splits = ceil_div(M, chunk);
     CLICA_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
-    SimtGemmParams q;
-    q.A = dy; q.a_sm = 1; q.a_sk = lddy;          // A(n, m) = dy[m][n]
-    q.B = x; q.b_sk = ldx; q.b_sn = 1;            // B(m, k) = x[m][k]
-    q.C = dW; q.ldc = lddw; q.M = N; q.N = K; q.K = M; q.k_chunk = chunk;
-    q.bias = nullptr; q.aux = nullptr; q.ldaux = 0; q.slope = 1.f; q.epilogue = kEpiAtomic;
-    dim3 grid(ceil_div(K, kSBN), ceil_div(N, kSBM), splits);
-    { LaunchScope ls(st, kFamGemmSimt); gemm_simt_kernel<false, false><<<grid, 256, 0, st>>>(q); }
-    CLICA_CUDA_OK(cudaGetLastError());
-    if (db) {
-        { LaunchScope ls(st, kFamMisc); colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, st>>>(dy, lddy, M, N, db); }
-        CLICA_CUDA_OK(cudaGetLastError());
-    }
+    SimtGemmParams q = {};
+    q.A = dy.hi; q.A_lo = dy.lo; q.a_sm = 1; q.a_sk = dy.ld;      // A(n, m) = dy[m][n]
+    q.B = x.hi; q.B_lo = x.lo; q.b_sk = x.ld; q.b_sn = 1;         // B(m, k) = x[m][k]
+    q.C = dW; q.C_lo = nullptr; q.ldc = lddw; q.M = N; q.N = K; q.K = M; q.k_chunk = chunk;
+    q.slope = 1.f; q.epilogue = kEpiAtomic;
+    int rc = simt_gemm(q, false, false, splits, st);
+    if (rc) return rc;
+    if (db) return simt_colsum(dy.hi, dy.lo, dy.ld, M, N, db, st);
     return 0;
 }
-
-namespace {
 
 bool tc_mode(int mode) { return mode == CLICA_GEMM_3XTF32 || mode == CLICA_GEMM_TF32; }
 bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -72,6 +86,70 @@ bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 int check_mode(int mode) {
     CLICA_REQUIRE(mode == CLICA_GEMM_3XTF32 || mode == CLICA_GEMM_TF32 || mode == CLICA_GEMM_FP32,
                   CLICA_E_BADARG, "unknown GEMM mode %d", mode);
+    return 0;
+}
+
+// ---- whole-stack planning ------------------------------------------------------------------------------
+struct MlpPlan {
+    int L; const int* w; int M; int mode;
+    int nplanes;                     // planes per hidden activation (2 in 3xTF32 mode, else 1)
+    bool planar;                     // hidden activations use plane_ld() pitches
+    bool layer_tc(int l) const {
+        return tc_mode(mode) && l > 0 && l < L - 1 && tc_shape_ok(M, w[l + 1], w[l]);
+    }
+    int act_ld(int l) const { return planar ? plane_ld(w[l]) : w[l]; }
+    size_t act_floats(int l) const { return (size_t)nplanes * M * act_ld(l); }
+    size_t wplane_floats(int l) const { return layer_tc(l) ? (size_t)nplanes * w[l + 1] * plane_ld(w[l]) : 0; }
+};
+MlpPlan make_plan(int L, const int* widths, int M, int mode) {
+    MlpPlan p;
+    p.L = L; p.w = widths; p.M = M; p.mode = mode;
+    p.planar = tc_mode(mode);
+    p.nplanes = (mode == CLICA_GEMM_3XTF32) ? 2 : 1;
+    return p;
+}
+PlanesIn act_in(const MlpPlan& p, const float* const* acts, int l) {
+    PlanesIn a;
+    if (l == 0 || l == p.L) { a.hi = acts[l]; a.lo = nullptr; a.ld = p.w[l]; return a; }
+    a.ld = p.act_ld(l);
+    a.hi = acts[l];
+    a.lo = (p.nplanes == 2) ? acts[l] + (size_t)p.M * a.ld : nullptr;
+    return a;
+}
+PlanesOut as_out(PlanesIn a) { PlanesOut o; o.hi = (float*)a.hi; o.lo = (float*)a.lo; o.ld = a.ld; return o; }
+
+struct MlpWs { float* wplanes[64]; float* gbuf[2]; size_t bytes; };
+MlpWs carve_mlp(const MlpPlan& p, void* ws) {
+    MlpWs w;
+    char* base = (char*)ws;
+    size_t off = 0;
+    size_t gmax = 0;
+    for (int l = 0; l < p.L && l < 64; ++l) {
+        w.wplanes[l] = (float*)(base + off);
+        off += align_up(p.wplane_floats(l) * sizeof(float), 1024);
+        if (l > 0 && p.act_floats(l) > gmax) gmax = p.act_floats(l);
+    }
+    for (int k = 0; k < 2; ++k) {
+        w.gbuf[k] = (float*)(base + off);
+        off += align_up(gmax * sizeof(float), 1024);
+    }
+    w.bytes = off;
+    return w;
+}
+PlanesIn weight_planes(const MlpPlan& p, const MlpWs& w, int l) {
+    PlanesIn a;
+    a.ld = plane_ld(p.w[l]);
+    a.hi = w.wplanes[l];
+    a.lo = (p.nplanes == 2) ? w.wplanes[l] + (size_t)p.w[l + 1] * a.ld : nullptr;
+    return a;
+}
+int pack_weights(const MlpPlan& p, const MlpWs& w, const float* const* W, cudaStream_t st) {
+    for (int l = 0; l < p.L; ++l) {
+        if (!p.layer_tc(l)) continue;
+        PlanesIn wp = weight_planes(p, w, l);
+        int rc = tc_split_planes(W[l], p.w[l], p.w[l + 1], p.w[l], (float*)wp.hi, (float*)wp.lo, wp.ld, st);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -96,10 +174,11 @@ extern "C" int clica_linear_act_fwd(const float* x, int ldx, const float* W, int
     DeviceInfo di;
     if ((rc = get_device_info(&di))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_mode(mode) && tc_shape_ok(M, N, K) && ldx % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0 &&
-        aligned16(x) && aligned16(W) && aligned16(y))
+    if (tc_mode(mode) && tc_shape_ok(M, N, K) && ldy % 4 == 0 && aligned16(y)) {
+        CLICA_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(M, N, K, mode), CLICA_E_WORKSPACE, "linear_act_fwd: workspace too small");
         return tc_linear_fwd(x, ldx, W, ldw, b, y, ldy, M, K, N, slope, mode, ws, ws_bytes, di.sm_count, st);
-    return simt_linear_fwd(x, ldx, W, ldw, b, y, ldy, M, K, N, slope, st);
+    }
+    return simt_fwd(PlanesIn{x, nullptr, ldx}, W, ldw, b, PlanesOut{y, nullptr, ldy}, M, K, N, slope, st);
 }
 
 extern "C" int clica_linear_act_bwd_data(const float* dy, int lddy, const float* W, int ldw,
@@ -114,11 +193,12 @@ extern "C" int clica_linear_act_bwd_data(const float* dy, int lddy, const float*
     DeviceInfo di;
     if ((rc = get_device_info(&di))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_mode(mode) && tc_shape_ok(M, K, N) && lddy % 4 == 0 && ldw % 4 == 0 && lddx % 4 == 0 &&
-        (!x_act || ldxa % 4 == 0) && aligned16(dy) && aligned16(W) && aligned16(dx))
+    if (tc_mode(mode) && tc_shape_ok(M, K, N) && lddx % 4 == 0 && aligned16(dx)) {
+        CLICA_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(M, N, K, mode), CLICA_E_WORKSPACE, "linear_act_bwd_data: workspace too small");
         return tc_linear_bwd_data(dy, lddy, W, ldw, x_act, ldxa, slope_prev, dx, lddx, M, K, N, mode, ws,
                                   ws_bytes, di.sm_count, st);
-    return simt_linear_bwd_data(dy, lddy, W, ldw, x_act, ldxa, slope_prev, dx, lddx, M, K, N, st);
+    }
+    return simt_bwd_data(PlanesIn{dy, nullptr, lddy}, W, ldw, x_act, ldxa, slope_prev, PlanesOut{dx, nullptr, lddx}, M, K, N, st);
 }
 
 extern "C" int clica_linear_bwd_weight(const float* dy, int lddy, const float* x, int ldx,
@@ -132,34 +212,53 @@ extern "C" int clica_linear_bwd_weight(const float* dy, int lddy, const float* x
     DeviceInfo di;
     if ((rc = get_device_info(&di))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_mode(mode) && tc_shape_ok(N, K, M) && lddy % 4 == 0 && ldx % 4 == 0 && lddw % 4 == 0 &&
-        aligned16(dy) && aligned16(x) && aligned16(dW))
+    if (tc_mode(mode) && tc_shape_ok(N, K, M)) {
+        CLICA_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(M, N, K, mode), CLICA_E_WORKSPACE, "linear_bwd_weight: workspace too small");
         return tc_linear_bwd_weight(dy, lddy, x, ldx, dW, lddw, db, M, K, N, mode, ws, ws_bytes, di.sm_count, st);
-    return simt_linear_bwd_weight(dy, lddy, x, ldx, dW, lddw, db, M, K, N, di.sm_count, st);
+    }
+    return simt_bwd_weight(PlanesIn{dy, nullptr, lddy}, PlanesIn{x, nullptr, ldx}, dW, lddw, db, M, K, N, di.sm_count, st);
 }
 
 // ---- whole-stack calls ----------------------------------------------------------------------------
+extern "C" size_t clica_mlp_act_floats(int M, int width, int mode) {
+    if (M < 1 || width < 1) return 0;
+    if (!tc_mode(mode)) return (size_t)M * width;
+    return (size_t)((mode == CLICA_GEMM_3XTF32) ? 2 : 1) * M * plane_ld(width);
+}
+
 extern "C" size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode) {
-    size_t need = 0;
-    size_t gbuf = 0;
-    for (int l = 0; l < L; ++l) {
-        size_t w = clica_linear_workspace_bytes(M, widths[l + 1], widths[l], mode);
-        if (w > need) need = w;
-        size_t g = (size_t)M * (size_t)widths[l] * sizeof(float);
-        if (l > 0 && g > gbuf) gbuf = g;
-    }
-    // backward ping-pong buffers for dL/d(acts[l]) + the per-layer GEMM workspace
-    return align_up(need, 1024) + 2 * align_up(gbuf, 1024);
+    if (L < 1 || L > 64 || !widths || M < 1) return 0;
+    MlpPlan p = make_plan(L, widths, M, mode);
+    return carve_mlp(p, nullptr).bytes + 1024;
 }
 
 extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, const float* const* b,
                              float* const* acts, int M, float slope, int mode,
                              void* ws, size_t ws_bytes, void* stream) {
-    CLICA_REQUIRE(L >= 1 && widths && W && b && acts, CLICA_E_BADARG, "mlp_fwd: null pointer / L < 1");
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    CLICA_REQUIRE(L >= 1 && L <= 64 && widths && W && b && acts && M >= 1, CLICA_E_BADARG, "mlp_fwd: bad arguments");
+    DeviceInfo di;
+    if ((rc = get_device_info(&di))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    MlpPlan p = make_plan(L, widths, M, mode);
+    void* wsa = (void*)align_up((size_t)(uintptr_t)ws, 1024);
+    MlpWs w = carve_mlp(p, wsa);
+    CLICA_REQUIRE(ws && ws_bytes >= w.bytes + 1024, CLICA_E_WORKSPACE, "mlp_fwd: workspace %zu < %zu bytes", ws_bytes, w.bytes + 1024);
+    if ((rc = pack_weights(p, w, W, st))) return rc;
     for (int l = 0; l < L; ++l) {
         const int K = widths[l], N = widths[l + 1];
         const float s = (l == L - 1) ? 1.f : slope;
-        int rc = clica_linear_act_fwd(acts[l], K, W[l], K, b[l], acts[l + 1], N, M, K, N, s, mode, ws, ws_bytes, stream);
+        PlanesIn x = act_in(p, acts, l);
+        PlanesOut y = as_out(act_in(p, acts, l + 1));
+        if (p.layer_tc(l)) {
+            TcGemm g = {};
+            g.A = x; g.a_mn_major = 0; g.B = weight_planes(p, w, l); g.b_mn_major = 0;
+            g.Mo = M; g.No = N; g.Kr = K; g.epi = kTcBiasAct; g.bias = b[l]; g.slope = s; g.outp = y;
+            rc = tc_gemm_launch(g, di.sm_count, st);
+        } else {
+            rc = simt_fwd(x, W[l], K, b[l], y, M, K, N, s, st);
+        }
         if (rc) return rc;
     }
     return 0;
@@ -168,34 +267,53 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
 extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, const float* const* acts,
                              const float* g_out, float* const* dW, float* const* db, float* g_in,
                              int M, float slope, int mode, void* ws, size_t ws_bytes, void* stream) {
-    CLICA_REQUIRE(L >= 1 && widths && W && acts && g_out && dW && db, CLICA_E_BADARG, "mlp_bwd: null pointer / L < 1");
-    size_t need = clica_mlp_workspace_bytes(M, L, widths, mode);
-    CLICA_REQUIRE(ws_bytes >= need && (need == 0 || ws), CLICA_E_WORKSPACE, "mlp_bwd: workspace %zu < %zu bytes", ws_bytes, need);
-    size_t gbuf = 0, lin = 0;
-    for (int l = 0; l < L; ++l) {
-        size_t w = clica_linear_workspace_bytes(M, widths[l + 1], widths[l], mode);
-        if (w > lin) lin = w;
-        size_t g = (size_t)M * (size_t)widths[l] * sizeof(float);
-        if (l > 0 && g > gbuf) gbuf = g;
-    }
-    char* base = (char*)ws;
-    void* lin_ws = base;
-    float* gb[2] = {(float*)(base + align_up(lin, 1024)), (float*)(base + align_up(lin, 1024) + align_up(gbuf, 1024))};
-    const float* g = g_out;   // dL/d acts[l+1] (already through the activation mask)
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    CLICA_REQUIRE(L >= 1 && L <= 64 && widths && W && acts && g_out && dW && db && M >= 1, CLICA_E_BADARG, "mlp_bwd: bad arguments");
+    DeviceInfo di;
+    if ((rc = get_device_info(&di))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    MlpPlan p = make_plan(L, widths, M, mode);
+    void* wsa = (void*)align_up((size_t)(uintptr_t)ws, 1024);
+    MlpWs w = carve_mlp(p, wsa);
+    CLICA_REQUIRE(ws && ws_bytes >= w.bytes + 1024, CLICA_E_WORKSPACE, "mlp_bwd: workspace %zu < %zu bytes", ws_bytes, w.bytes + 1024);
+    if ((rc = pack_weights(p, w, W, st))) return rc;
+
+    PlanesIn g = {g_out, nullptr, widths[L]};     // dL/d(pre-activation of layer l), starts as dL/d(output)
     for (int l = L - 1; l >= 0; --l) {
         const int K = widths[l], N = widths[l + 1];
-        int rc = clica_linear_bwd_weight(g, N, acts[l], K, dW[l], K, db[l], M, K, N, mode, lin_ws, lin, stream);
-        if (rc) return rc;
-        if (l > 0) {
-            float* gx = gb[l & 1];
-            // acts[l] is the LeakyReLU output of layer l-1: its sign is the activation mask
-            rc = clica_linear_act_bwd_data(g, N, W[l], K, acts[l], K, slope, gx, K, M, K, N, mode, lin_ws, lin, stream);
-            if (rc) return rc;
-            g = gx;
-        } else if (g_in) {
-            rc = clica_linear_act_bwd_data(g, N, W[0], K, nullptr, 0, 1.f, g_in, K, M, K, N, mode, lin_ws, lin, stream);
-            if (rc) return rc;
+        PlanesIn x = act_in(p, acts, l);
+        // dW[l] = g^T x ; db[l] = column sums of g
+        if (p.layer_tc(l)) {
+            CLICA_CUDA_OK(cudaMemsetAsync(dW[l], 0, (size_t)N * K * sizeof(float), st));
+            TcGemm t = {};
+            t.A = g; t.a_mn_major = 1; t.B = x; t.b_mn_major = 1;
+            t.Mo = N; t.No = K; t.Kr = M; t.epi = kTcAtomic; t.out = dW[l]; t.ldo = K; t.allow_split_k = 1;
+            if ((rc = tc_gemm_launch(t, di.sm_count, st))) return rc;
+            if ((rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st))) return rc;
+        } else {
+            if ((rc = simt_bwd_weight(g, x, dW[l], K, db[l], M, K, N, di.sm_count, st))) return rc;
         }
+        if (l == 0) {
+            if (g_in) rc = simt_bwd_data(g, W[0], K, nullptr, 0, 1.f, PlanesOut{g_in, nullptr, K}, M, K, N, st);
+            if (rc) return rc;
+            break;
+        }
+        // g_prev = (g W[l]) * LeakyReLU'(pre-activation of layer l-1); acts[l] = LeakyReLU output: same sign
+        PlanesOut gp;
+        gp.ld = p.act_ld(l);
+        gp.hi = w.gbuf[l & 1];
+        gp.lo = (p.nplanes == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
+        if (p.layer_tc(l)) {
+            TcGemm t = {};
+            t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1;
+            t.Mo = M; t.No = K; t.Kr = N; t.epi = kTcMask; t.aux = x.hi; t.ldaux = x.ld; t.slope = slope; t.outp = gp;
+            rc = tc_gemm_launch(t, di.sm_count, st);
+        } else {
+            rc = simt_bwd_data(g, W[l], K, x.hi, x.ld, slope, gp, M, K, N, st);
+        }
+        if (rc) return rc;
+        g.hi = gp.hi; g.lo = gp.lo; g.ld = gp.ld;
     }
     return 0;
 }

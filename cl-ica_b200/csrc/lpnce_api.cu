@@ -35,7 +35,7 @@ struct FinParams {
     const float* part_m; const float* part_s; int part_stride; int nsplit;
     const float* z1; int ld1; const float* z2; int ld2;
     int B; int M; int d; float p; float tau; float alpha; int include_pos;
-    float* loss_i; float* lse; float* pos; float* scalars;
+    float* loss_i; float* lse; float* pos; float2* rowstat; float* scalars;
     double* block_sums; int* counter;
 };
 
@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) 
         float S = q.include_pos ? exp2f(xp - M) : 0.f;
         for (int sidx = 0; sidx < q.nsplit; ++sidx)
             S += q.part_s[(size_t)sidx * q.part_stride + i] * exp2f(q.part_m[(size_t)sidx * q.part_stride + i] - M);
-        float l = (M + log2f(S)) * kLn2;
+        const float ls = log2f(S);
+        q.rowstat[i] = make_float2(M, ls);
+        float l = (M + ls) * kLn2;
         if (!q.include_pos) l -= logf((float)q.M);
         const float li = 2.f * (q.alpha * ps / q.tau + (1.f - q.alpha) * l);
         q.loss_i[i] = li;
@@ -91,12 +93,12 @@ __global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) 
     }
 }
 
-// per-anchor coefficients of the backward:  L2 = log2-domain (un-shifted) lse, E = 2 gl (1-alpha)/tau,
-// CP = 2 gl (alpha - (1-alpha) w+)/tau,  gl_i = g_mean * inv_count + g_loss_i[i]
+// per-anchor coefficients of the backward:  E = 2 gl (1-alpha)/tau,  CP = 2 gl (alpha - (1-alpha) w+)/tau,
+// gl_i = g_mean * inv_count + g_loss_i[i],  w+ = exp2((-pos*coef - m2) - ls) from the forward's row statistics
 struct PrepParams {
-    const float* lse; const float* pos; const float* g_mean; const float* g_loss_i;
-    int n; float inv_count; float shift; float tau; float alpha; int include_pos;
-    float* L2; float* E; float* CP;   // CP nullable (then pos is not read)
+    const float2* rowstat; const float* pos; const float* g_mean; const float* g_loss_i;
+    int n; float inv_count; float tau; float alpha; int include_pos;
+    float* E; float* CP;              // either may be null (CP null: pos / rowstat are not read)
     float default_g;                  // used when g_mean == nullptr
 };
 __global__ void lpnce_prep_kernel(const PrepParams q) {
@@ -104,11 +106,10 @@ __global__ void lpnce_prep_kernel(const PrepParams q) {
     if (i >= q.n) return;
     float gl = (q.g_mean ? *q.g_mean : q.default_g) * q.inv_count;
     if (q.g_loss_i) gl += q.g_loss_i[i];
-    const float l2 = (q.lse[i] + q.shift) * kLog2e;
-    if (q.L2) q.L2[i] = l2;
     if (q.E) q.E[i] = 2.f * gl * (1.f - q.alpha) / q.tau;
     if (q.CP) {
-        const float wpos = q.include_pos ? exp2f(-q.pos[i] * (kLog2e / q.tau) - l2) : 0.f;
+        const float2 st = q.rowstat[i];
+        const float wpos = q.include_pos ? exp2f(fmaf(q.pos[i], -(kLog2e / q.tau), -st.x) - st.y) : 0.f;
         q.CP[i] = 2.f * gl * (q.alpha - (1.f - q.alpha) * wpos) / q.tau;
     }
 }
@@ -234,13 +235,12 @@ FwdWs carve_fwd(void* ws, int B, int nsplit) {
     return w;
 }
 
-struct BwdWs { float* L2; float* E; float* CP; float* partA; float* partB; size_t bytes; };
-// nL = entries of L2/E (B for the plain backward, M for the sharded one)
+struct BwdWs { float* E; float* CP; float* partA; float* partB; size_t bytes; };
+// nL = entries of E (B for the plain backward, M for the sharded one)
 BwdWs carve_bwd(void* ws, int nL, int B, int rowsA, int nsA, int rowsB, int nsB, int TW) {
     BwdWs w;
     char* p = (char*)ws;
     size_t off = 0;
-    w.L2 = (float*)(p + off); off += align_up((size_t)nL * sizeof(float), 16);
     w.E = (float*)(p + off); off += align_up((size_t)nL * sizeof(float), 16);
     w.CP = (float*)(p + off); off += align_up((size_t)B * sizeof(float), 16);
     w.partA = (float*)(p + off); off += align_up((size_t)nsA * rowsA * TW * sizeof(float), 16);
@@ -268,12 +268,13 @@ extern "C" size_t clica_lpnce_workspace_bytes(int B, int M, int d) {
 
 extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
                                int B, int M, int d, float p, float tau, float alpha, int include_pos,
-                               int use_pow, float* loss_i, float* lse, float* pos, float* scalars3,
-                               void* ws, size_t ws_bytes, void* stream) {
+                               int use_pow, float* loss_i, float* lse, float* pos, float* rowstat,
+                               float* scalars3, void* ws, size_t ws_bytes, void* stream) {
     int DP; DeviceInfo di;
     int rc = check_common(B, M, d, p, tau, use_pow, &DP, &di);
     if (rc) return rc;
-    CLICA_REQUIRE(z1 && z2 && z3 && loss_i && lse && pos && scalars3 && ws, CLICA_E_BADARG, "lpnce_fwd: null pointer");
+    CLICA_REQUIRE(z1 && z2 && z3 && loss_i && lse && pos && rowstat && scalars3 && ws, CLICA_E_BADARG, "lpnce_fwd: null pointer");
+    CLICA_REQUIRE(((uintptr_t)rowstat & 7u) == 0, CLICA_E_ALIGN, "lpnce_fwd: rowstat must be 8-byte aligned");
     CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d, CLICA_E_BADARG, "lpnce_fwd: leading dimension < d");
     CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_fwd: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -293,7 +294,7 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
     f.part_m = w.part_m; f.part_s = w.part_s; f.part_stride = B; f.nsplit = pl.nsplit;
     f.z1 = z1; f.ld1 = ld1; f.z2 = z2; f.ld2 = ld2; f.B = B; f.M = M; f.d = d; f.p = p; f.tau = tau;
     f.alpha = alpha; f.include_pos = include_pos;
-    f.loss_i = loss_i; f.lse = lse; f.pos = pos; f.scalars = scalars3;
+    f.loss_i = loss_i; f.lse = lse; f.pos = pos; f.rowstat = (float2*)rowstat; f.scalars = scalars3;
     f.block_sums = w.block_sums; f.counter = w.counter;
     { LaunchScope ls(st, kFamLossAux); lpnce_finalize_kernel<<<ceil_div(B, 256), 256, 0, st>>>(f); }
     CLICA_CUDA_OK(cudaGetLastError());
@@ -310,13 +311,14 @@ extern "C" size_t clica_lpnce_bwd_workspace_bytes(int B, int M, int d) {
 
 extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
                                int B, int M, int d, float p, float tau, float alpha, int include_pos,
-                               int use_pow, const float* lse, const float* pos, const float* g_mean,
+                               int use_pow, const float* rowstat, const float* pos, const float* g_mean,
                                const float* g_loss_i, float* g_z1, int ldg1, float* g_z2, int ldg2,
                                float* g_z3, int ldg3, void* ws, size_t ws_bytes, void* stream) {
     int DP; DeviceInfo di;
     int rc = check_common(B, M, d, p, tau, use_pow, &DP, &di);
     if (rc) return rc;
-    CLICA_REQUIRE(z1 && z2 && z3 && lse && pos && ws, CLICA_E_BADARG, "lpnce_bwd: null pointer");
+    CLICA_REQUIRE(z1 && z2 && z3 && rowstat && pos && ws, CLICA_E_BADARG, "lpnce_bwd: null pointer");
+    CLICA_REQUIRE(((uintptr_t)rowstat & 7u) == 0, CLICA_E_ALIGN, "lpnce_bwd: rowstat must be 8-byte aligned");
     CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d, CLICA_E_BADARG, "lpnce_bwd: leading dimension < d");
     CLICA_REQUIRE((!g_z1 || ldg1 >= d) && (!g_z2 || ldg2 >= d) && (!g_z3 || ldg3 >= d), CLICA_E_BADARG,
                   "lpnce_bwd: gradient leading dimension < d");
@@ -328,10 +330,10 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
     CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_bwd: workspace %zu < %zu bytes", ws_bytes, w.bytes);
 
     PrepParams pp;
-    pp.lse = lse; pp.pos = pos; pp.g_mean = g_mean; pp.g_loss_i = g_loss_i; pp.n = B;
-    pp.inv_count = 1.f / (float)B; pp.shift = include_pos ? 0.f : logf((float)M);
+    pp.rowstat = (const float2*)rowstat; pp.pos = pos; pp.g_mean = g_mean; pp.g_loss_i = g_loss_i; pp.n = B;
+    pp.inv_count = 1.f / (float)B;
     pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
-    pp.L2 = w.L2; pp.E = w.E; pp.CP = w.CP; pp.default_g = 0.f;
+    pp.E = w.E; pp.CP = w.CP; pp.default_g = 0.f;
     { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
 
@@ -343,7 +345,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         if (needA) {   // anchors own, negatives stream
             BwdRole& r = q.role[q.nroles++];
             r.O = z1; r.ldO = ld1; r.BO = B; r.S = z3; r.ldS = ld3; r.MS = M;
-            r.LO = w.L2; r.LS = nullptr; r.ES = nullptr;
+            r.LO = (const float2*)rowstat; r.LS = nullptr; r.ES = nullptr;
             r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z3, ld3, d, DP);
             r.part = w.partA; r.part_rows = B; r.row_tiles = pa.row_tiles;
             gx = max(gx, pa.row_tiles); gy = max(gy, pa.nsplit);
@@ -351,7 +353,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         if (needB) {   // negatives own, anchors (with their lse and coefficient) stream
             BwdRole& r = q.role[q.nroles++];
             r.O = z3; r.ldO = ld3; r.BO = M; r.S = z1; r.ldS = ld1; r.MS = B;
-            r.LO = nullptr; r.LS = w.L2; r.ES = w.E;
+            r.LO = nullptr; r.LS = (const float2*)rowstat; r.ES = w.E;
             r.tiles_per_split = pb.tiles_per_split; r.nsplit = pb.nsplit; r.flat16 = is_flat16(z1, ld1, d, DP);
             r.part = w.partB; r.part_rows = M; r.row_tiles = pb.row_tiles;
             gx = max(gx, pb.row_tiles); gy = max(gy, pb.nsplit);
@@ -393,7 +395,7 @@ extern "C" size_t clica_lpnce_bwd_sharded_workspace_bytes(int B, int M, int d) {
 }
 
 extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const float* z2_local, int ld2,
-                                       const float* z_all, int ld3, const float* lse_all,
+                                       const float* z_all, int ld3, const float* rowstat_all,
                                        const float* pos_local, int B, int M, int d, int row0, float p,
                                        float tau, float alpha, int include_pos, const float* g_scale,
                                        float* g_z1, int ldg1, float* g_z2, int ldg2,
@@ -401,8 +403,9 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     int DP; DeviceInfo di;
     int rc = check_common(B, M, d, p, tau, 1, &DP, &di);
     if (rc) return rc;
-    CLICA_REQUIRE(z1_local && z2_local && z_all && lse_all && pos_local && g_z1 && ws, CLICA_E_BADARG,
+    CLICA_REQUIRE(z1_local && z2_local && z_all && rowstat_all && pos_local && g_z1 && ws, CLICA_E_BADARG,
                   "lpnce_bwd_sharded: null pointer");
+    CLICA_REQUIRE(((uintptr_t)rowstat_all & 7u) == 0, CLICA_E_ALIGN, "lpnce_bwd_sharded: rowstat must be 8-byte aligned");
     CLICA_REQUIRE(row0 >= 0 && row0 + B <= M, CLICA_E_BADARG, "lpnce_bwd_sharded: rows [%d, %d) outside [0, %d)", row0, row0 + B, M);
     CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d && ldg1 >= d && (!g_z2 || ldg2 >= d), CLICA_E_BADARG,
                   "lpnce_bwd_sharded: leading dimension < d");
@@ -415,14 +418,15 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
 
     // coefficients of every global anchor (they all stream through the column-role pass) ...
     PrepParams pp;
-    pp.lse = lse_all; pp.pos = nullptr; pp.g_mean = g_scale; pp.g_loss_i = nullptr; pp.n = M;
-    pp.inv_count = 1.f / (float)M; pp.shift = include_pos ? 0.f : logf((float)M);
+    const float2* stat_all = (const float2*)rowstat_all;
+    pp.rowstat = stat_all; pp.pos = nullptr; pp.g_mean = g_scale; pp.g_loss_i = nullptr; pp.n = M;
+    pp.inv_count = 1.f / (float)M;
     pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
-    pp.L2 = w.L2; pp.E = w.E; pp.CP = nullptr; pp.default_g = 1.f;
+    pp.E = w.E; pp.CP = nullptr; pp.default_g = 1.f;
     { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
     // ... and the positive-pair coefficient of the local rows
-    pp.lse = lse_all + row0; pp.pos = pos_local; pp.n = B; pp.L2 = nullptr; pp.E = nullptr; pp.CP = w.CP;
+    pp.rowstat = stat_all + row0; pp.pos = pos_local; pp.n = B; pp.E = nullptr; pp.CP = w.CP;
     { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
 
@@ -435,8 +439,8 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
         r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = flat;
         r.part_rows = B; r.row_tiles = pa.row_tiles;
     }
-    q.role[0].LO = w.L2 + row0; q.role[0].LS = nullptr; q.role[0].ES = nullptr; q.role[0].part = w.partA;   // local rows as anchors
-    q.role[1].LO = nullptr; q.role[1].LS = w.L2; q.role[1].ES = w.E; q.role[1].part = w.partB;             // local rows as negatives
+    q.role[0].LO = stat_all + row0; q.role[0].LS = nullptr; q.role[0].ES = nullptr; q.role[0].part = w.partA;   // local rows as anchors
+    q.role[1].LO = nullptr; q.role[1].LS = stat_all; q.role[1].ES = w.E; q.role[1].part = w.partB;             // local rows as negatives
     { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 2), st); }
     if (rc) return rc;
 

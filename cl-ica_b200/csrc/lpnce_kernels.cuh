@@ -40,7 +40,7 @@ inline size_t fwd_smem_bytes(int DP, int R) {
     return tiles > merge ? tiles : merge;
 }
 inline size_t bwd_smem_bytes(int DP, int R) {
-    size_t tiles = 2ull * (kTN * 2 * DP + 2 * kTN) * sizeof(float);
+    size_t tiles = 2ull * (kTN * 2 * DP + 4 * kTN) * sizeof(float);
     size_t merge = (size_t)(kCW - 1) * (kWarps / kCW) * R * DP * 32 * sizeof(float2);
     return tiles > merge ? tiles : merge;
 }
@@ -54,12 +54,16 @@ struct FwdParams {
     int* counter;                        // zeroed here for the finalize kernel's last-block reduction
 };
 
-// w(owner i, streamed j) = ES[j] * exp2( -D * coef - LO[i] - LS[j] );  gacc_i += w * G'(s_j - o_i)/p
+// Row statistics of the forward, per anchor: (m2, ls) = (reference maximum of the log2-domain logits,
+// log2 of the sum of exp2(logit - m2)); the soft-max weight of a pair is exp2((-D*coef - m2) - ls), i.e. the
+// SAME arithmetic the forward used, so the weights of a row sum to 1 to fp32 accuracy however large |lse| is.
+// w(owner i, streamed j) = ES[j] * exp2( (-D*coef - m2) - ls ), (m2, ls) taken from the owner (anchor role)
+// or from the streamed row (column role);  gacc_i += w * G'(s_j - o_i)/p
 struct BwdRole {
     const float* O; int ldO; int BO;
     const float* S; int ldS; int MS;
-    const float* LO;                   // owner log2-domain lse (nullable -> 0)
-    const float* LS; const float* ES;  // streamed log2-domain lse and coefficient (both or neither)
+    const float2* LO;                   // owner row statistics (nullable -> (0, 0))
+    const float2* LS; const float* ES;  // streamed row statistics and coefficient (both or neither)
     int tiles_per_split; int nsplit; int flat16;
     float* part; int part_rows;        // [nsplit][part_rows][2*DP]
     int row_tiles;
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
     constexpr int ROWS = 32 * R * RW;
     constexpr int TW = 2 * DP;
     constexpr int CPW = kTN / CW;
-    constexpr int TILE_FLOATS = kTN * TW + 2 * kTN;   // features + (LS, ES) per streamed row
+    constexpr int TILE_FLOATS = kTN * TW + 4 * kTN;   // features + (m2, ls, ES, pad) per streamed row
     extern __shared__ __align__(16) float smem[];
     const BwdRole& ro = q.role[blockIdx.z];
     if ((int)blockIdx.x >= ro.row_tiles || (int)blockIdx.y >= ro.nsplit) return;
@@ -302,14 +306,15 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
 
     float2 na[R][DP];
     float2 gacc[R][DP];
-    float lo[R];
+    float lo_m[R], lo_s[R];
     load_owner_rows<DP, R>(na, ro.O, ro.ldO, ro.BO, q.d, row_base, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int row = row_base + r * 32 + lane;
 #pragma unroll
         for (int c = 0; c < DP; ++c) gacc[r][c] = make_float2(0.f, 0.f);
-        lo[r] = (ro.LO != nullptr && row < ro.BO) ? __ldg(ro.LO + row) : 0.f;
+        const float2 st = (ro.LO != nullptr && row < ro.BO) ? __ldg(ro.LO + row) : make_float2(0.f, 0.f);
+        lo_m[r] = st.x; lo_s[r] = st.y;
     }
 
     const int ntiles = (ro.MS + kTN - 1) / kTN;
@@ -322,9 +327,11 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         if (has_ss && tid < kTN) {
             const int j = t * kTN + tid;
             const bool ok = j < ro.MS;
-            float* sdst = dst + kTN * TW + 2 * tid;
-            cp_async_4(sdst, ok ? (const void*)(ro.LS + j) : (const void*)ro.LS, ok ? 4 : 0);
-            cp_async_4(sdst + 1, ok ? (const void*)(ro.ES + j) : (const void*)ro.ES, ok ? 4 : 0);
+            float* sdst = dst + kTN * TW + 4 * tid;
+            const float* stat = reinterpret_cast<const float*>(ro.LS);
+            cp_async_4(sdst, ok ? (const void*)(stat + 2 * j) : (const void*)stat, ok ? 4 : 0);
+            cp_async_4(sdst + 1, ok ? (const void*)(stat + 2 * j + 1) : (const void*)stat, ok ? 4 : 0);
+            cp_async_4(sdst + 2, ok ? (const void*)(ro.ES + j) : (const void*)ro.ES, ok ? 4 : 0);   // 0 for tail rows
         }
         cp_async_commit();
     };
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         else cp_async_wait<0>();
         __syncthreads();
         const float* tile = smem + stage * TILE_FLOATS;
-        const float2* ss = reinterpret_cast<const float2*>(tile + kTN * TW);
+        const float4* ss = reinterpret_cast<const float4*>(tile + kTN * TW);
         const int nvalid = min(kTN, ro.MS - t * kTN);
         const int c_end = min(cw * CPW + CPW, nvalid);
         for (int kk = cw * CPW; kk < c_end; kk += 2) {
@@ -349,10 +356,11 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
                 bb[2 * c + 1] = make_float2(v.z, v.w);
             }
             const bool has1 = (kk + 1 < c_end);
-            float ls0 = 0.f, ls1 = 0.f, es0 = 1.f, es1 = has1 ? 1.f : 0.f;
+            float sm0 = 0.f, sm1 = 0.f, sl0 = 0.f, sl1 = 0.f, es0 = 1.f, es1 = has1 ? 1.f : 0.f;
             if (has_ss) {
-                const float4 sv = *reinterpret_cast<const float4*>(ss + kk);   // (LS0, ES0, LS1, ES1)
-                ls0 = sv.x; es0 = sv.y; ls1 = sv.z; es1 = has1 ? sv.w : 0.f;
+                const float4 s0 = ss[kk], s1 = ss[kk + 1];   // (m2, ls, ES, -)
+                sm0 = s0.x; sl0 = s0.y; es0 = s0.z;
+                sm1 = s1.x; sl1 = s1.y; es1 = has1 ? s1.z : 0.f;
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -362,8 +370,9 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
                     a0 = Lp<P>::accum(__fadd2_rn(bb[c], na[r][c]), a0, q.pg);
                     a1 = Lp<P>::accum(__fadd2_rn(bb[DP + c], na[r][c]), a1, q.pg);
                 }
-                const float w0 = es0 * ex2_approx(fmaf(a0.x + a0.y, -q.coef, -(lo[r] + ls0)));
-                const float w1 = es1 * ex2_approx(fmaf(a1.x + a1.y, -q.coef, -(lo[r] + ls1)));
+                // exactly one of (owner, streamed) statistics is non-zero; m2 is subtracted inside the fma
+                const float w0 = es0 * ex2_approx(fmaf(a0.x + a0.y, -q.coef, -(lo_m[r] + sm0)) - (lo_s[r] + sl0));
+                const float w1 = es1 * ex2_approx(fmaf(a1.x + a1.y, -q.coef, -(lo_m[r] + sm1)) - (lo_s[r] + sl1));
 #pragma unroll
                 for (int c = 0; c < DP; ++c) {
                     gacc[r][c] = Lp<P>::grad(w0, __fadd2_rn(bb[c], na[r][c]), gacc[r][c], q.pg);

@@ -71,16 +71,17 @@ class _LpInfoNCE(torch.autograd.Function):
             raise RuntimeError(f"shape mismatch: z1 {tuple(z1.shape)}, z2 {tuple(z2.shape)}, z3 {tuple(z3.shape)}")
         dev = z1.device
         with torch.cuda.device(dev):
-            out = torch.empty(3 * B + 3, dtype=torch.float32, device=dev)
-            loss_i, lse, pos, scal = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:]
+            # one allocation: rowstat[B][2] first (8-byte aligned), then loss_i, lse, pos, scalars[3]
+            out = torch.empty(5 * B + 3, dtype=torch.float32, device=dev)
+            rowstat, loss_i, lse, pos, scal = out[:2 * B], out[2 * B:3 * B], out[3 * B:4 * B], out[4 * B:5 * B], out[5 * B:]
             nbytes = lib.clica_lpnce_workspace_bytes(B, M, d)
             ws = _workspace(nbytes, dev, "lpnce")
             rc = lib.clica_lpnce_fwd(z1.data_ptr(), _ld(z1), z2.data_ptr(), _ld(z2), z3.data_ptr(), _ld(z3),
                                      B, M, d, float(p), float(tau), float(alpha), int(include_pos), 1,
-                                     loss_i.data_ptr(), lse.data_ptr(), pos.data_ptr(), scal.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                                     loss_i.data_ptr(), lse.data_ptr(), pos.data_ptr(), rowstat.data_ptr(),
+                                     scal.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_lpnce_fwd")
-        ctx.save_for_backward(z1, z2, z3, lse, pos)
+        ctx.save_for_backward(z1, z2, z3, rowstat, pos)
         ctx.cfg = (float(p), float(tau), float(alpha), int(include_pos))
         ctx.set_materialize_grads(False)
         mean, pos_mean, neg_mean = scal[0], scal[1], scal[2]
@@ -90,7 +91,7 @@ class _LpInfoNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mean, g_loss_i, _g_pos, _g_neg):
         lib = _lib.load()
-        z1, z2, z3, lse, pos = ctx.saved_tensors
+        z1, z2, z3, rowstat, pos = ctx.saved_tensors
         p, tau, alpha, include_pos = ctx.cfg
         B, d = z1.shape
         M = z3.shape[0]
@@ -109,7 +110,7 @@ class _LpInfoNCE(torch.autograd.Function):
             nbytes = lib.clica_lpnce_bwd_workspace_bytes(B, M, d)
             ws = _workspace(nbytes, dev, "lpnce_bwd")
             rc = lib.clica_lpnce_bwd(z1.data_ptr(), _ld(z1), z2.data_ptr(), _ld(z2), z3.data_ptr(), _ld(z3),
-                                     B, M, d, p, tau, alpha, include_pos, 1, lse.data_ptr(), pos.data_ptr(),
+                                     B, M, d, p, tau, alpha, include_pos, 1, rowstat.data_ptr(), pos.data_ptr(),
                                      _ptr(g_mean), _ptr(g_loss_i), _ptr(g1), d, _ptr(g2), d, _ptr(g3), d,
                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_lpnce_bwd")
@@ -150,7 +151,11 @@ class _MLP(torch.autograd.Function):
         M = x.shape[0]
         dev = x.device
         with torch.cuda.device(dev):
-            acts = [x] + [torch.empty((M, w), dtype=torch.float32, device=dev) for w in widths[1:]]
+            # hidden activations are opaque buffers in the GEMM operand format of `mode` (see include/clica.h)
+            acts = [x]
+            for w in widths[1:-1]:
+                acts.append(torch.empty(lib.clica_mlp_act_floats(M, w, int(mode)), dtype=torch.float32, device=dev))
+            acts.append(torch.empty((M, widths[-1]), dtype=torch.float32, device=dev))
             cw = (ctypes.c_int * (L + 1))(*widths)
             nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
             ws = _workspace(nbytes, dev, "mlp")

@@ -7,8 +7,8 @@ exactly those semantics -- every anchor sees ALL negatives of the global batch -
   rank r owns anchors/positives [r*B/W, (r+1)*B/W)
   fwd : a_r = f(g(z1_r)), b_r = f(g(z2_r))          encoder on the local shard
         z_all   = all_gather(a_r)                   (B_global x d, 0.25 .. 1.3 MB: latency-bound)
-        loss_i, lse, pos = lpnce_fwd(a_r, b_r, z_all)        local rows x all columns
-        lse_all = all_gather(lse)                   (B_global floats)
+        loss_i, lse, pos, rowstat = lpnce_fwd(a_r, b_r, z_all)   local rows x all columns
+        rowstat_all = all_gather(rowstat)           (B_global x 2 floats: row max + log2 sum)
         loss    = all_reduce(sum_i loss_i) / B_global
   bwd : g_a, g_b = lpnce_bwd_sharded(...)           anchor-role + column-role + positive terms for the
                                                     LOCAL rows, already scaled by 1/B_global: no
@@ -28,7 +28,7 @@ from . import _lib
 
 # ---- kernel access (CUDA) ---------------------------------------------------------------------------------
 def local_forward(z1_local, z2_local, z_all, p, tau, alpha, include_pos) -> Tuple[torch.Tensor, ...]:
-    """(loss_i, lse, pos) of the local anchors against all gathered rows (clica_lpnce_fwd)."""
+    """(loss_i, lse, pos, rowstat[B,2]) of the local anchors against all gathered rows (clica_lpnce_fwd)."""
     from . import functional as F
     lib = _lib.load()
     z1, z2, za = F._as_rows(z1_local, "z1_local"), F._as_rows(z2_local, "z2_local"), F._as_rows(z_all, "z_all")
@@ -36,17 +36,17 @@ def local_forward(z1_local, z2_local, z_all, p, tau, alpha, include_pos) -> Tupl
     M = za.shape[0]
     dev = z1.device
     with torch.cuda.device(dev):
-        out = torch.empty(3 * B + 3, dtype=torch.float32, device=dev)
+        out = torch.empty(5 * B + 3, dtype=torch.float32, device=dev)
         ws = F._workspace(lib.clica_lpnce_workspace_bytes(B, M, d), dev, "lpnce")
         rc = lib.clica_lpnce_fwd(z1.data_ptr(), F._ld(z1), z2.data_ptr(), F._ld(z2), za.data_ptr(), F._ld(za),
                                  B, M, d, float(p), float(tau), float(alpha), int(include_pos), 1,
-                                 out.data_ptr(), out[B:].data_ptr(), out[2 * B:].data_ptr(), out[3 * B:].data_ptr(),
-                                 ws.data_ptr(), ws.numel(), F._stream_ptr(dev))
+                                 out[2 * B:].data_ptr(), out[3 * B:].data_ptr(), out[4 * B:].data_ptr(),
+                                 out.data_ptr(), out[5 * B:].data_ptr(), ws.data_ptr(), ws.numel(), F._stream_ptr(dev))
         _lib.check(rc, "clica_lpnce_fwd")
-    return out[:B], out[B:2 * B], out[2 * B:3 * B]
+    return out[2 * B:3 * B], out[3 * B:4 * B], out[4 * B:5 * B], out[:2 * B].view(B, 2)
 
 
-def local_backward(z1_local, z2_local, z_all, lse_all, pos_local, row0, p, tau, alpha, include_pos,
+def local_backward(z1_local, z2_local, z_all, rowstat_all, pos_local, row0, p, tau, alpha, include_pos,
                    g_scale: Optional[torch.Tensor] = None):
     """Gradient of the GLOBAL mean loss w.r.t. the local anchors / positives (clica_lpnce_bwd_sharded)."""
     from . import functional as F
@@ -55,7 +55,7 @@ def local_backward(z1_local, z2_local, z_all, lse_all, pos_local, row0, p, tau, 
     B, d = z1.shape
     M = za.shape[0]
     dev = z1.device
-    lse_all = lse_all.contiguous()
+    rowstat_all = rowstat_all.contiguous()
     pos_local = pos_local.contiguous()
     with torch.cuda.device(dev):
         g1 = torch.empty((B, d), dtype=torch.float32, device=dev)
@@ -64,7 +64,7 @@ def local_backward(z1_local, z2_local, z_all, lse_all, pos_local, row0, p, tau, 
             g_scale = g_scale.to(device=dev, dtype=torch.float32).contiguous()
         ws = F._workspace(lib.clica_lpnce_bwd_sharded_workspace_bytes(B, M, d), dev, "lpnce_bwd")
         rc = lib.clica_lpnce_bwd_sharded(z1.data_ptr(), F._ld(z1), z2.data_ptr(), F._ld(z2), za.data_ptr(), F._ld(za),
-                                         lse_all.data_ptr(), pos_local.data_ptr(), B, M, d, int(row0), float(p),
+                                         rowstat_all.data_ptr(), pos_local.data_ptr(), B, M, d, int(row0), float(p),
                                          float(tau), float(alpha), int(include_pos),
                                          None if g_scale is None else g_scale.data_ptr(),
                                          g1.data_ptr(), d, g2.data_ptr(), d, ws.data_ptr(), ws.numel(),
@@ -92,21 +92,21 @@ class _ShardedInfoNCE(torch.autograd.Function):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         a_det, b_det = a_local.detach(), b_local.detach()
         z_all = _all_gather_rows(a_det, group)
-        loss_i, lse, pos = ops.local_forward(a_det, b_det, z_all, p, tau, alpha, include_pos)
-        lse_all = _all_gather_rows(lse, group)
+        loss_i, lse, pos, rowstat = ops.local_forward(a_det, b_det, z_all, p, tau, alpha, include_pos)
+        rowstat_all = _all_gather_rows(rowstat, group)
         stats = torch.stack([loss_i.sum(), pos.sum() / tau, lse.sum()])
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
         stats = stats / z_all.shape[0]
-        ctx.save_for_backward(a_det, b_det, z_all, lse_all, pos)
+        ctx.save_for_backward(a_det, b_det, z_all, rowstat_all, pos)
         ctx.cfg = (p, tau, alpha, include_pos, rank * a_local.shape[0], ops)
         ctx.mark_non_differentiable(loss_i)
         return stats[0], loss_i, stats[1:].detach()
 
     @staticmethod
     def backward(ctx, g_mean, _g_li, _g_parts):
-        a, b, z_all, lse_all, pos = ctx.saved_tensors
+        a, b, z_all, rowstat_all, pos = ctx.saved_tensors
         p, tau, alpha, include_pos, row0, ops = ctx.cfg
-        g1, g2 = ops.local_backward(a, b, z_all, lse_all, pos, row0, p, tau, alpha, include_pos, g_mean)
+        g1, g2 = ops.local_backward(a, b, z_all, rowstat_all, pos, row0, p, tau, alpha, include_pos, g_mean)
         return g1, g2, None, None, None, None, None, None
 
 

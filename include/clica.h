@@ -64,18 +64,22 @@ CLICA_API int         clica_device_info(int* sm_count, int* cc_major, int* cc_mi
  * shared memory, the row soft-max is evaluated online.
  *
  * outputs  loss_i[B], lse[B] (as defined above), pos[B] (un-scaled pos_i),
+ *          rowstat[B][2] = per anchor (m2, ls): the reference maximum of the log2-domain logits and the
+ *          log2 of the sum of exp2(logit - m2).  The backward re-derives every soft-max weight as
+ *          exp2((-D*log2(e)/tau - m2) - ls) -- the forward's own arithmetic -- so a row's weights sum to 1 to
+ *          fp32 accuracy even when |lse| is in the thousands (8-byte aligned),
  *          scalars[3] = { mean_i loss_i, mean_i pos_i/tau, mean_i lse_i }   (losses.py:469-477)
  * p        any real >= 1; p in {1,2,3,4} use multiply-only inner loops, other p use ex2/lg2.
  * use_pow  must be 1 (losses.py:452-454, `pow=True`, the only value any reference script uses).
  * ws       scratch of at least clica_lpnce_workspace_bytes(B, M, d) bytes, 16-byte aligned (split
- *          partials; dead after the call -- the backward is stateless and takes lse / pos back).
+ *          partials; dead after the call -- the backward is stateless and takes rowstat / pos back).
  * ---------------------------------------------------------------------------------------------- */
 CLICA_API size_t clica_lpnce_workspace_bytes(int B, int M, int d);
 
 CLICA_API int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
                     int B, int M, int d, float p, float tau, float alpha, int include_pos,
-                    int use_pow, float* loss_i, float* lse, float* pos, float* scalars3,
-                    void* ws, size_t ws_bytes, void* stream);
+                    int use_pow, float* loss_i, float* lse, float* pos, float* rowstat,
+                    float* scalars3, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Lp-InfoNCE loss, backward.        replaces  autograd through losses.py:447-477
@@ -85,7 +89,7 @@ CLICA_API int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2
  * Gradient of  L = g_mean * mean_i loss_i + sum_i g_loss_i[i] * loss_i  with respect to z1, z2, z3.
  *   g_mean    device scalar (nullable => 0):  dL/d scalars3[0]
  *   g_loss_i  device [B]    (nullable => 0):  dL/d loss_i
- *   lse, pos  the forward's outputs
+ *   rowstat, pos  the forward's outputs
  *   g_z1[B,d] (ld = ldg1), g_z2[B,d], g_z3[M,d]: any may be NULL (skipped).  g_z1 receives only the
  *             anchor-role term; a caller whose z3 aliases z1 (torch.roll, main_mlp.py:272) adds g_z3
  *             back through its own autograd graph exactly as the reference does.
@@ -96,23 +100,23 @@ CLICA_API size_t clica_lpnce_bwd_workspace_bytes(int B, int M, int d);
 
 CLICA_API int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
                     int B, int M, int d, float p, float tau, float alpha, int include_pos,
-                    int use_pow, const float* lse, const float* pos, const float* g_mean,
+                    int use_pow, const float* rowstat, const float* pos, const float* g_mean,
                     const float* g_loss_i, float* g_z1, int ldg1, float* g_z2, int ldg2,
                     float* g_z3, int ldg3, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-sharded variant (one process per GPU).  The caller all-gathers the encoder
  * outputs (NCCL) so that z_all[M,d] holds every rank's anchors, runs clica_lpnce_fwd on its own rows
- * [row0, row0+B) against z_all, all-gathers lse into lse_all[M], then calls this: it returns, for the
+ * [row0, row0+B) against z_all, all-gathers rowstat into rowstat_all[M][2], then calls this: it returns, for the
  * LOCAL rows only, the complete gradient of the GLOBAL mean loss  (1/M) sum_i loss_i  with
  * z3 = roll(z_all, 1):   anchor-role term + column-role term (rows i of every rank that use local
- * row k as a negative, weights exp(-D_ik/tau - lse_all[i])) + positive term.  No second collective.
+ * row k as a negative, weights from rowstat_all[i]) + positive term.  No second collective.
  *   g_scale  device scalar: dL/d(global mean loss)   (nullable => 1)
  * ---------------------------------------------------------------------------------------------- */
 CLICA_API size_t clica_lpnce_bwd_sharded_workspace_bytes(int B, int M, int d);
 
 CLICA_API int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const float* z2_local, int ld2,
-                            const float* z_all, int ld3, const float* lse_all,
+                            const float* z_all, int ld3, const float* rowstat_all,
                             const float* pos_local, int B, int M, int d, int row0, float p,
                             float tau, float alpha, int include_pos, const float* g_scale,
                             float* g_z1, int ldg1, float* g_z2, int ldg2,
@@ -154,12 +158,17 @@ CLICA_API int clica_linear_bwd_weight(const float* dy, int lddy, const float* x,
  * pays one FFI crossing instead of 7 / 20).            replaces  encoders.py:36-58 forward + autograd
  *
  * Layer l (0 <= l < L): W[l] is [widths[l+1], widths[l]] (ld = widths[l]), b[l] is [widths[l+1]].
- * acts[l] (l = 0..L) are caller-allocated [M, widths[l]] dense buffers: acts[0] = input x,
- * acts[L] = output; the hidden ones are what the backward needs (saved by the caller's autograd ctx).
- * LeakyReLU(slope) after every layer but the last.
+ * acts[l] (l = 0..L) are caller-allocated: acts[0] = input x and acts[L] = output are dense
+ * [M, widths[l]] fp32; the hidden ones (0 < l < L) are OPAQUE buffers of clica_mlp_act_floats(M,
+ * widths[l], mode) floats, 16-byte aligned, holding the activation in the GEMM operand format of `mode`
+ * ((hi, lo) planes in 3xTF32 mode) -- they are what the backward needs (saved by the caller's autograd
+ * ctx) and are never converted.  LeakyReLU(slope) after every layer but the last.
  * backward: g_out = dL/d acts[L]; dW[l], db[l] are written (not accumulated); g_in nullable
  * (main_mlp.py feeds the frozen mixing net's output, which needs no gradient).
+ * The first and last layer (n -> 10n, 10n -> n: rows TMA cannot address, <2% of the flops) always run on
+ * the exact-fp32 CUDA-core kernel; hidden layers with M, K, N >= 32 run on tcgen05 in tensor-core modes.
  * ---------------------------------------------------------------------------------------------- */
+CLICA_API size_t clica_mlp_act_floats(int M, int width, int mode);
 CLICA_API size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode);
 
 CLICA_API int clica_mlp_fwd(int L, const int* widths, const float* const* W, const float* const* b,

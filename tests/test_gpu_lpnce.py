@@ -64,14 +64,14 @@ def test_pow_false_is_refused_not_approximated(cuda_device):
     from clica_b200 import _lib
     lib = _lib.load()
     a = torch.randn(8, 4, device=cuda_device)
-    out = torch.empty(8 * 3 + 3, device=cuda_device)
+    out = torch.empty(8 * 5 + 3, device=cuda_device)
     ws = torch.empty(1 << 16, dtype=torch.uint8, device=cuda_device)
     rc = lib.clica_lpnce_fwd(a.data_ptr(), 4, a.data_ptr(), 4, a.data_ptr(), 4, 8, 8, 4, 2.0, 1.0, 0.5, 1, 0,
-                             out.data_ptr(), out[8:].data_ptr(), out[16:].data_ptr(), out[24:].data_ptr(),
+                             out[16:].data_ptr(), out[24:].data_ptr(), out[32:].data_ptr(), out.data_ptr(), out[40:].data_ptr(),
                              ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     assert rc == -2 and b"pow=False" in lib.clica_last_error()
     rc = lib.clica_lpnce_fwd(a.data_ptr(), 4, a.data_ptr(), 4, a.data_ptr(), 4, 8, 8, 4, 0.5, 1.0, 0.5, 1, 1,
-                             out.data_ptr(), out[8:].data_ptr(), out[16:].data_ptr(), out[24:].data_ptr(),
+                             out[16:].data_ptr(), out[24:].data_ptr(), out[32:].data_ptr(), out.data_ptr(), out[40:].data_ptr(),
                              ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     assert rc == -2
 
@@ -187,11 +187,11 @@ def test_sharded_backward_equals_single_device(cuda_device):
     mean, per_item, _, _ = F.lp_infonce(a, b, torch.roll(a, 1, 0), p, tau, 0.5, True)
     mean.backward()
     Bl = B // W
-    lse_parts, pos_parts, loss_parts = [], [], []
+    stat_parts, pos_parts, loss_parts = [], [], []
     for r in range(W):
-        li, lse, pos = sharded.local_forward(z1[r * Bl:(r + 1) * Bl], z2[r * Bl:(r + 1) * Bl], z1, p, tau, 0.5, True)
-        lse_parts.append(lse), pos_parts.append(pos), loss_parts.append(li)
-    lse_all = torch.cat(lse_parts)
+        li, lse, pos, stat = sharded.local_forward(z1[r * Bl:(r + 1) * Bl], z2[r * Bl:(r + 1) * Bl], z1, p, tau, 0.5, True)
+        stat_parts.append(stat.clone()), pos_parts.append(pos.clone()), loss_parts.append(li.clone())
+    lse_all = torch.cat(stat_parts)
     assert (torch.cat(loss_parts) - per_item.detach()).abs().max().item() <= 2e-6 * max(1.0, per_item.abs().max().item())
     for r in range(W):
         g1, g2 = sharded.local_backward(z1[r * Bl:(r + 1) * Bl], z2[r * Bl:(r + 1) * Bl], z1, lse_all, pos_parts[r],
