@@ -223,79 +223,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // tcgen05.ld hands every thread 32 consecutive columns of ITS row; storing that directly would touch 32
+        // different cache lines per instruction.  Each warp therefore transposes its 32 x 32 chunk through a
+        // padded shared-memory tile (the pipeline stages are dead by now) and walks it row by row, so that every
+        // global access of the epilogue (bias, mask, plain / hi / lo stores, split-K atomics) is one 128-byte line.
         const int wq = warp & 3;
-        const int row = m0 + wq * 32 + lane;
         mbar_wait(&tmem_full_bar, 0u);
         tcgen05_fence_after();
-        const bool row_ok = row < q.Mo;
+        float* stg = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + wq * (32 * 33);
+        const int row0 = m0 + wq * 32;
+        const int nrows = min(32, q.Mo - row0);
 #pragma unroll 1
         for (int chunk = 0; chunk < BN / 32; ++chunk) {
             float v[32];
-            __syncwarp();   // tcgen05.ld is .sync.aligned: re-converge after the divergent stores / continues below
+            __syncwarp();   // previous chunk's readers are done with stg; tcgen05.ld is .sync.aligned
             tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chunk * 32), v);
-            const int col0 = n0 + chunk * 32;
-            const int nvalid = min(32, q.No - col0);
-            if (!row_ok || nvalid <= 0) continue;
-            if (q.epi == kTcBiasAct) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = v[j];
-                    if (q.bias != nullptr && j < nvalid) t += __ldg(q.bias + col0 + j);
-                    v[j] = t > 0.f ? t : t * q.slope;
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];      // bank (lane + j) % 32: conflict-free
+            __syncwarp();
+            const int col = n0 + chunk * 32 + lane;
+            if (col >= q.No || nrows <= 0) continue;
+            const float bias_v = (q.epi == kTcBiasAct && q.bias != nullptr) ? __ldg(q.bias + col) : 0.f;
+            for (int r = 0; r < nrows; ++r) {
+                float t = stg[r * 33 + lane];
+                const size_t grow = (size_t)(row0 + r);
+                if (q.epi == kTcAtomic) {
+                    atomicAdd(q.out + grow * q.ldo + col, t);
+                    continue;
                 }
-            } else if (q.epi == kTcMask) {
-                if (q.aux != nullptr) {
-                    const float* ap = q.aux + (size_t)row * q.ldaux + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) v[j] *= (__ldg(ap + j) > 0.f) ? 1.f : q.slope;
+                if (q.epi == kTcBiasAct) {
+                    t += bias_v;
+                    t = t > 0.f ? t : t * q.slope;
+                } else if (q.aux != nullptr) {
+                    t *= (__ldg(q.aux + grow * q.ldaux + col) > 0.f) ? 1.f : q.slope;
                 }
-            } else {
-                float* op = q.out + (size_t)row * q.ldo + col0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < nvalid) atomicAdd(op + j, v[j]);
-                continue;
-            }
-            if (q.out != nullptr) {
-                float* op = q.out + (size_t)row * q.ldo + col0;
-                if (nvalid == 32 && (q.ldo & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) op[j] = v[j];
-                }
-            }
-            if (q.out_hi != nullptr) {
-                float* hp = q.out_hi + (size_t)row * q.ldp + col0;
-                float* lp = (q.out_lo != nullptr) ? q.out_lo + (size_t)row * q.ldp + col0 : nullptr;
-                if (lp != nullptr) {
-                    if (nvalid == 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 h, l;
-                            h.x = round_to_tf32(v[j]); l.x = v[j] - h.x;
-                            h.y = round_to_tf32(v[j + 1]); l.y = v[j + 1] - h.y;
-                            h.z = round_to_tf32(v[j + 2]); l.z = v[j + 2] - h.z;
-                            h.w = round_to_tf32(v[j + 3]); l.w = v[j + 3] - h.w;
-                            *reinterpret_cast<float4*>(hp + j) = h;
-                            *reinterpret_cast<float4*>(lp + j) = l;
-                        }
+                if (q.out != nullptr) q.out[grow * q.ldo + col] = t;
+                if (q.out_hi != nullptr) {
+                    if (q.out_lo != nullptr) {
+                        const float h = round_to_tf32(t);
+                        q.out_hi[grow * q.ldp + col] = h;
+                        q.out_lo[grow * q.ldp + col] = t - h;
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) { const float h = round_to_tf32(v[j]); hp[j] = h; lp[j] = v[j] - h; }
-                    }
-                } else {
-                    if (nvalid == 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(hp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) hp[j] = v[j];
+                        q.out_hi[grow * q.ldp + col] = t;
                     }
                 }
             }
