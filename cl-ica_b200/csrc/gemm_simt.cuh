@@ -29,6 +29,7 @@ struct SimtGemmParams {
     const float* aux; int ldaux;
     float slope;
     int epilogue;
+    float* colsum;           // optional [N]: += column sums of the stored values (kEpiMask only; caller zeroes it)
 };
 
 #ifdef __CUDACC__
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtGemmParams 
         }
     }
 
+    float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -134,13 +136,21 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtGemmParams 
             } else if (q.aux) {
                 v *= (__ldg(q.aux + (size_t)m * q.ldaux + n) > 0.f) ? 1.f : q.slope;
             }
+            csum[j] += v;
             if (q.C_lo) {
                 const float h = round_to_tf32(v);
                 q.C[o] = h;
-                q.C_lo[o] = v - h;
+                q.C_lo[o] = round_to_tf32(v - h);
             } else {
                 q.C[o] = v;
             }
+        }
+    }
+    if (q.colsum != nullptr && q.epilogue == kEpiMask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n < q.N) atomicAdd(q.colsum + n, csum[j]);
         }
     }
 }

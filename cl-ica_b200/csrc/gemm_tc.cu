@@ -1,15 +1,17 @@
 // gemm_tc.cu -- hand-written tcgen05 GEMM for the encoder's Linear layers (sm_100a).
 //
-//   D[128 x 128 tile] = sum_r A(m, r) B(n, r)          fp32 operands consumed as TF32 by tcgen05.mma kind::tf32
+//   D[128 x BN tile] = sum_r A(m, r) B(n, r)           fp32 operands consumed as TF32 by tcgen05.mma kind::tf32
 //
 // Replaces the cuBLAS SGEMMs behind nn.Linear fwd / AddmmBackward of /root/reference/encoders.py:39.
 //
-// Structure (one output tile per CTA, 192 threads):
+// Structure (persistent: one CTA per SM loops over output tiles; 192 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor.2d (128B-swizzled boxes) -> smem ring, mbarrier complete_tx
-//   warp 1      MMA issuer    : one elected thread issues tcgen05.mma (M=128, N=128, K=8) from smem descriptors,
-//                               accumulator in TMEM (128 columns x 128 lanes fp32); tcgen05.commit frees the stage
-//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> fused
-//                               bias + LeakyReLU | activation mask | split-K atomic accumulate -> global
+//   warp 1      MMA issuer    : one elected thread issues tcgen05.mma (M=128, N=BN in {128, 256}, K=8) from smem
+//                               descriptors; fp32 accumulators double-buffered in TMEM (2 x BN columns x 128
+//                               lanes); tcgen05.commit recycles smem stages and publishes finished accumulators
+//   warps 2..9  epilogue      : tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> fused
+//                               bias + LeakyReLU | activation mask | split-K atomic accumulate -> global,
+//                               overlapped with the next tile's main loop
 // Both operand majors are supported natively (instruction-descriptor a_major / b_major bits, MN-major
 // 128B-swizzle shared-memory descriptors), so forward (x W^T), backward-data (dY W) and backward-weight
 // (dY^T X) all read the row-major tensors as they lie in HBM: no transposes are ever materialised.
@@ -27,15 +29,13 @@
 namespace clica {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;             // BK fp32 = 128 bytes = one swizzle span
-constexpr int kTileBytes = BM * BK * 4;                // 16 KiB per operand plane per stage
-constexpr int kTcThreads = 192;
-constexpr int kTmemCols = 128;
+constexpr int BM = 128, BK = 32;                       // BK fp32 = 128 bytes = one swizzle span; BN = 128 or 256 (template)
+constexpr int kTcThreads = 320;                          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
 
 struct TcKernelParams {
     int Mo, No;
-    int kb_total, kb_per_split;
+    int kb_total, kb_per_split, splits;
     int a_mn, b_mn, nterms, stages;
     int epi;
     const float* bias; float slope;
@@ -43,6 +43,7 @@ struct TcKernelParams {
     float* out; int ldo;
     float* out_hi; float* out_lo; int ldp;
     uint32_t mn_lbo, mn_sbo, mn_lt;   // MN-major descriptor fields (defaults: BK*128, 512, 1)
+    float* colsum;                    // optional [No]: += column sums of the stored values (pre-zeroed by the caller)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -53,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -88,6 +92,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -125,22 +133,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)layout_type << 61;
     return d;
 }
-// instruction descriptor: D fp32, A/B tf32, M = 128, N = 128
-__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn) {
+// instruction descriptor: D fp32, A/B tf32, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// one operand tile of a stage: K-major = one {32 x 128} box; MN-major = four {32 x 32} boxes
+// one operand tile of a stage: K-major = one {32 x ROWS} box; MN-major = ROWS/32 boxes of {32 x 32}
+template <int ROWS>
 __device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar) {
     if (!mn_major) {
         tma_load_2d(dst, tm, k0, mn0, bar);
     } else {
 #pragma unroll
-        for (int j = 0; j < BM / 32; ++j) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
+        for (int j = 0; j < ROWS / 32; ++j) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
     }
 }
 
+// Persistent kernel: grid = min(#work items, #SMs); a work item is (split, n-tile, m-tile) with m fastest so that
+// CTAs running side by side share the B tile in L2.  The accumulator is double-buffered in TMEM (2 x BN columns),
+// so the epilogue of item i overlaps the main loop of item i+1; the smem ring runs continuously across items.
+template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -148,24 +161,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[BN];
 
+    constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-byte alignment
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzled tiles need 1024-byte alignment
     const int nplanes = (q.nterms == 3) ? 2 : 1;
-    const uint32_t stage_bytes = 2u * nplanes * kTileBytes;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kb0 = blockIdx.z * q.kb_per_split;
-    const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
-    const int nkb = kb1 - kb0;
+    const uint32_t stage_bytes = (uint32_t)nplanes * (kABytes + kBBytes);
+    const int num_m = (q.Mo + BM - 1) / BM, num_n = (q.No + BN - 1) / BN;
+    const int total = num_m * num_n * q.splits;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < q.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, kTmemCols);
+    if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -174,107 +188,222 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % q.stages;
-                const uint32_t ph = (uint32_t)(i / q.stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                const uint32_t sa = tiles + s * stage_bytes;
-                const int k0 = (kb0 + i) * BK;
-                load_operand(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s]);
-                if (nplanes == 2) load_operand(&tmAl, sa + kTileBytes, q.a_mn, m0, k0, &full_bar[s]);
-                load_operand(&tmBh, sa + nplanes * kTileBytes, q.b_mn, n0, k0, &full_bar[s]);
-                if (nplanes == 2) load_operand(&tmBl, sa + (nplanes + 1) * kTileBytes, q.b_mn, n0, k0, &full_bar[s]);
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int m0 = (w % num_m) * BM;
+                const int rest = w / num_m;
+                const int n0 = (rest % num_n) * BN;
+                const int kb0 = (rest / num_n) * q.kb_per_split;
+                const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)q.stages;
+                    const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    const uint32_t sa = tiles + s * stage_bytes;
+                    const uint32_t sb = sa + nplanes * kABytes;
+                    const int k0 = kb * BK;
+                    load_operand<BM>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s]);
+                    if (nplanes == 2) load_operand<BM>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s]);
+                    load_operand<BN>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s]);
+                    if (nplanes == 2) load_operand<BN>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s]);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc(q.a_mn, q.b_mn);
+            const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, BN);
             const uint32_t a_step = q.a_mn ? 1024u : 32u, b_step = q.b_mn ? 1024u : 32u;   // bytes per K = 8 step
             const uint32_t a_lbo = q.a_mn ? q.mn_lbo : 16u, b_lbo = q.b_mn ? q.mn_lbo : 16u;
             const uint32_t a_sbo = q.a_mn ? q.mn_sbo : 1024u, b_sbo = q.b_mn ? q.mn_sbo : 1024u;
             const uint32_t a_lt = q.a_mn ? q.mn_lt : 2u, b_lt = q.b_mn ? q.mn_lt : 2u;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % q.stages;
-                const uint32_t ph = (uint32_t)(i / q.stages) & 1u;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, tile_iter = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
+                const int rest = w / num_m;
+                const int kb0 = (rest / num_n) * q.kb_per_split;
+                const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
+                const uint32_t as = tile_iter & 1u;
+                mbar_wait(&tmem_empty_bar[as], ((tile_iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t sa = tiles + s * stage_bytes;
-                const uint32_t a_hi = sa, a_lo = sa + kTileBytes;
-                const uint32_t b_hi = sa + nplanes * kTileBytes, b_lo = sa + (nplanes + 1) * kTileBytes;
+                const uint32_t tmem_acc = tmem_base + as * (uint32_t)BN;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)q.stages;
+                    const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = tiles + s * stage_bytes;
+                    const uint32_t a_hi = sa, a_lo = sa + kABytes;
+                    const uint32_t b_hi = sa + nplanes * kABytes, b_lo = b_hi + kBBytes;
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t dah = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
-                    const uint64_t dbh = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
-                    if (nplanes == 2) {
-                        const uint64_t dal = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
-                        const uint64_t dbl = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-                        umma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
-                    } else {
-                        umma_tf32(tmem_base, dah, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        const uint64_t dah = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
+                        const uint64_t dbh = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+                        if (nplanes == 2) {
+                            const uint64_t dal = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+                            const uint64_t dbl = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+                            umma_tf32(tmem_acc, dal, dbh, idesc, first);   // small terms first
+                            umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+                            umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_acc, dah, dbh, idesc, first);
+                        }
                     }
+                    umma_commit(&empty_bar[s]);            // stage reusable once these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
+                umma_commit(&tmem_full_bar[as]);           // accumulator complete
             }
-            umma_commit(&tmem_full_bar);           // accumulator complete
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        // tcgen05.ld hands every thread 32 consecutive columns of ITS row; storing that directly would touch 32
-        // different cache lines per instruction.  Each warp therefore transposes its 32 x 32 chunk through a
-        // padded shared-memory tile (the pipeline stages are dead by now) and walks it row by row, so that every
-        // global access of the epilogue (bias, mask, plain / hi / lo stores, split-K atomics) is one 128-byte line.
+        // ===== epilogue: warps 2..9 (8 warps).  TMEM lane quarter = warp % 4; the two warps of a quarter take the
+        // even / odd 32-column chunks.  The epilogue is latency-bound (TMEM load -> global mask load -> stores), so:
+        //   * twice the warps = twice the memory-level parallelism,
+        //   * the bias slice of the tile is staged in shared memory once per tile (broadcast LDS instead of LDG),
+        //   * the activation-mask values of the NEXT chunk are prefetched while the current one is processed,
+        //   * every thread owns 32 consecutive columns of its row = one full 128-byte line, written with 8 STG.128
+        //     (split-K accumulation: 8 x red.global.add.v4.f32).
+        const int ew = warp - 2;
         const int wq = warp & 3;
-        mbar_wait(&tmem_full_bar, 0u);
-        tcgen05_fence_after();
-        float* stg = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + wq * (32 * 33);
-        const int row0 = m0 + wq * 32;
-        const int nrows = min(32, q.Mo - row0);
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-            float v[32];
-            __syncwarp();   // previous chunk's readers are done with stg; tcgen05.ld is .sync.aligned
-            tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chunk * 32), v);
+        const int half = ew >> 2;
+        const int etid = threadIdx.x - 64;                     // 0..255 among the epilogue threads
+        const bool aux_vec = (q.aux != nullptr) && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15u) == 0);
+        uint32_t tile_iter = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
+            const int m0 = (w % num_m) * BM;
+            const int n0 = ((w / num_m) % num_n) * BN;
+            const uint32_t as = tile_iter & 1u;
+            const int row = m0 + wq * 32 + lane;
+            const bool row_ok = row < q.Mo;
+            const int rowc = row_ok ? row : (q.Mo - 1);         // clamped: loads stay in bounds, stores are predicated
+            if (q.epi == kTcBiasAct) {
+                epi_bar_sync();                                 // previous tile's readers are done with bias_s
+                if (etid < BN) bias_s[etid] = (q.bias != nullptr && n0 + etid < q.No) ? __ldg(q.bias + n0 + etid) : 0.f;
+                epi_bar_sync();
+            }
+            const float* arow = (q.aux != nullptr) ? q.aux + (size_t)rowc * q.ldaux : nullptr;
+            float4 av[8];
+            auto load_aux = [&](int chunk) {                    // mask source for columns [n0 + 32*chunk, +32) of this row
+                const int c0 = n0 + chunk * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];      // bank (lane + j) % 32: conflict-free
-            __syncwarp();
-            const int col = n0 + chunk * 32 + lane;
-            if (col >= q.No || nrows <= 0) continue;
-            const float bias_v = (q.epi == kTcBiasAct && q.bias != nullptr) ? __ldg(q.bias + col) : 0.f;
-            for (int r = 0; r < nrows; ++r) {
-                float t = stg[r * 33 + lane];
-                const size_t grow = (size_t)(row0 + r);
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + 4 * j;
+                    if (aux_vec) {
+                        av[j] = (c < q.ldaux) ? __ldg(reinterpret_cast<const float4*>(arow + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        av[j].x = (c < q.No) ? __ldg(arow + c) : 0.f;
+                        av[j].y = (c + 1 < q.No) ? __ldg(arow + c + 1) : 0.f;
+                        av[j].z = (c + 2 < q.No) ? __ldg(arow + c + 2) : 0.f;
+                        av[j].w = (c + 3 < q.No) ? __ldg(arow + c + 3) : 0.f;
+                    }
+                }
+            };
+            const bool use_aux = (q.epi == kTcMask) && (q.aux != nullptr);
+            if (use_aux) load_aux(half);
+            mbar_wait(&tmem_full_bar[as], (tile_iter >> 1) & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int chunk = half; chunk < BN / 32; chunk += 2) {
+                float v[32];
+                __syncwarp();   // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
+                tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + as * (uint32_t)BN + (uint32_t)(chunk * 32), v);
+                const int col0 = n0 + chunk * 32;
+                const int nvalid = min(32, q.No - col0);
+                if (q.epi == kTcBiasAct) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(&bias_s[chunk * 32 + j]);
+                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * q.slope;
+                } else if (use_aux) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[4 * j] *= av[j].x > 0.f ? 1.f : q.slope; v[4 * j + 1] *= av[j].y > 0.f ? 1.f : q.slope;
+                        v[4 * j + 2] *= av[j].z > 0.f ? 1.f : q.slope; v[4 * j + 3] *= av[j].w > 0.f ? 1.f : q.slope;
+                    }
+                    if (chunk + 2 < BN / 32) load_aux(chunk + 2);       // prefetch for the next iteration
+                }
+                if (nvalid <= 0) continue;                              // warp-uniform
+                if (q.colsum != nullptr && q.epi != kTcAtomic) {
+                    // bias gradient of the layer whose pre-activation gradient this is: butterfly-reduce each column
+                    // over the warp's 32 rows (rows past M contribute 0), lane j keeps column j
+                    float mine = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float tot = warp_sum(row_ok ? v[j] : 0.f);
+                        if (lane == j) mine = tot;
+                    }
+                    if (lane < nvalid) atomicAdd(q.colsum + col0 + lane, mine);
+                }
+                if (!row_ok) continue;
                 if (q.epi == kTcAtomic) {
-                    atomicAdd(q.out + grow * q.ldo + col, t);
+                    float* op = q.out + (size_t)row * q.ldo + col0;
+                    if (nvalid == 32 && (q.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(q.out) & 15u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) red_add_v4(op + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) atomicAdd(op + j, v[j]);
+                    }
                     continue;
                 }
-                if (q.epi == kTcBiasAct) {
-                    t += bias_v;
-                    t = t > 0.f ? t : t * q.slope;
-                } else if (q.aux != nullptr) {
-                    t *= (__ldg(q.aux + grow * q.ldaux + col) > 0.f) ? 1.f : q.slope;
-                }
-                if (q.out != nullptr) q.out[grow * q.ldo + col] = t;
-                if (q.out_hi != nullptr) {
-                    if (q.out_lo != nullptr) {
-                        const float h = round_to_tf32(t);
-                        q.out_hi[grow * q.ldp + col] = h;
-                        q.out_lo[grow * q.ldp + col] = t - h;
+                if (q.out != nullptr) {
+                    float* op = q.out + (size_t)row * q.ldo + col0;
+                    if (nvalid == 32 && (q.ldo & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
-                        q.out_hi[grow * q.ldp + col] = t;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) op[j] = v[j];
+                    }
+                }
+                if (q.out_hi != nullptr) {
+                    float* hp = q.out_hi + (size_t)row * q.ldp + col0;
+                    float* lp = (q.out_lo != nullptr) ? q.out_lo + (size_t)row * q.ldp + col0 : nullptr;
+                    if (lp != nullptr) {
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 h, l;
+                                h.x = round_to_tf32(v[j]); l.x = round_to_tf32(v[j] - h.x);
+                                h.y = round_to_tf32(v[j + 1]); l.y = round_to_tf32(v[j + 1] - h.y);
+                                h.z = round_to_tf32(v[j + 2]); l.z = round_to_tf32(v[j + 2] - h.z);
+                                h.w = round_to_tf32(v[j + 3]); l.w = round_to_tf32(v[j + 3] - h.w);
+                                *reinterpret_cast<float4*>(hp + j) = h;
+                                *reinterpret_cast<float4*>(lp + j) = l;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) { const float h = round_to_tf32(v[j]); hp[j] = h; lp[j] = round_to_tf32(v[j] - h); }
+                        }
+                    } else {
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(hp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) hp[j] = v[j];
+                        }
                     }
                 }
             }
+            // this warp has read its share of the accumulator: hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
-        tcgen05_fence_before();
     }
+    tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
@@ -288,7 +417,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     if (lo != nullptr) {
         const float h = round_to_tf32(v);
         hi[idx] = h;
-        lo[idx] = v - h;
+        lo[idx] = round_to_tf32(v - h);   // rounded (not truncated by the MMA): keeps the split unbiased
     } else {
         hi[idx] = v;
     }
@@ -382,12 +511,17 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     CLICA_REQUIRE(g.Mo >= 1 && g.No >= 1 && g.Kr >= 1, CLICA_E_BADARG, "tc_gemm: empty problem");
     CLICA_REQUIRE(g.A.hi && g.B.hi, CLICA_E_BADARG, "tc_gemm: null operand");
     CLICA_REQUIRE((g.A.lo != nullptr) == (g.B.lo != nullptr), CLICA_E_BADARG, "tc_gemm: operands must both be split or both plain");
+    CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
     const int nterms = g.A.lo ? 3 : 1;
+    const int nplanes = (nterms == 3) ? 2 : 1;
+    // N = 256 per tcgen05.mma runs the tensor pipe at its peak rate (128 cycles; N = 128 takes 80.6, i.e. 79%:
+    // tools/mma_probe.cu) and needs 25% less operand traffic per flop; narrow outputs keep the 128-wide tile.
+    const int bn = (env_int("CLICA_TC_BN", g.No > 128 ? 256 : 128) == 256) ? 256 : 128;
     CUtensorMap tAh, tAl, tBh, tBl;
     int rc;
-    // storage shape of each operand: K-major [MN rows][Kr cols] (box 128 rows); MN-major [Kr rows][MN cols] (box 32 rows)
+    // storage shape of each operand: K-major [MN rows][Kr cols] (box = tile rows); MN-major [Kr rows][MN cols] (box 32 rows)
     const int a_rows = g.a_mn_major ? g.Kr : g.Mo, a_cols = g.a_mn_major ? g.Mo : g.Kr, a_box = g.a_mn_major ? BK : BM;
-    const int b_rows = g.b_mn_major ? g.Kr : g.No, b_cols = g.b_mn_major ? g.No : g.Kr, b_box = g.b_mn_major ? BK : BN;
+    const int b_rows = g.b_mn_major ? g.Kr : g.No, b_cols = g.b_mn_major ? g.No : g.Kr, b_box = g.b_mn_major ? BK : bn;
     if ((rc = get_tensor_map(g.A.hi, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAh))) return rc;
     if ((rc = get_tensor_map(g.B.hi, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBh))) return rc;
     if (nterms == 3) {
@@ -400,14 +534,17 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     q.Mo = g.Mo; q.No = g.No;
     q.kb_total = ceil_div(g.Kr, BK);
     q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms;
-    q.stages = (nterms == 3) ? 3 : 6;
+    const size_t stage_bytes = (size_t)nplanes * (BM + bn) * BK * 4;
+    const size_t smem_budget = 196 * 1024;                      // + 18 KB of epilogue staging + alignment slack < 227 KB
+    q.stages = (int)(smem_budget / stage_bytes);
+    if (q.stages > kMaxStages) q.stages = kMaxStages;
     q.epi = g.epi; q.bias = g.bias; q.slope = g.slope; q.aux = g.aux; q.ldaux = g.ldaux;
     q.out = g.out; q.ldo = g.ldo; q.out_hi = g.outp.hi; q.out_lo = g.outp.lo; q.ldp = g.outp.ld;
     q.mn_lbo = (uint32_t)env_int("CLICA_TC_MN_LBO", BK * 128);   // debug overrides of the MN-major descriptor
     q.mn_sbo = (uint32_t)env_int("CLICA_TC_MN_SBO", 512);
     q.mn_lt = (uint32_t)env_int("CLICA_TC_MN_LT", 1);
-    CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
-    const int tiles = ceil_div(g.Mo, BM) * ceil_div(g.No, BN);
+    q.colsum = g.colsum;
+    const int tiles = ceil_div(g.Mo, BM) * ceil_div(g.No, bn);
     int splits = 1;
     if (g.epi == kTcAtomic && g.allow_split_k) {
         splits = (sm_count + tiles - 1) / tiles;
@@ -417,14 +554,21 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     }
     q.kb_per_split = ceil_div(q.kb_total, splits);
     splits = ceil_div(q.kb_total, q.kb_per_split);
-    const size_t smem = (size_t)q.stages * 2 * (nterms == 3 ? 2 : 1) * kTileBytes + 1024;
+    q.splits = splits;
+    const size_t smem = (size_t)q.stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
-    dim3 grid(ceil_div(g.No, BN), ceil_div(g.Mo, BM), splits);
-    { LaunchScope ls(st, kFamGemmTc); gemm_tc_kernel<<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, q); }
+    const int total = tiles * splits;
+    const int grid = total < sm_count ? total : sm_count;
+    {
+        LaunchScope ls(st, kFamGemmTc);
+        if (bn == 256) gemm_tc_kernel<256><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, q);
+        else gemm_tc_kernel<128><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, q);
+    }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }

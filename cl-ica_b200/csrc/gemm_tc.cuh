@@ -28,12 +28,14 @@ struct TcGemm {
     float* out; int ldo;          // plain fp32 output (nullable unless epi == kTcAtomic)
     PlanesOut outp;               // planar output (hi = round-to-tf32(v), lo = v - hi), nullable
     int allow_split_k;            // epi == kTcAtomic only
+    float* colsum;                // optional [No]: += column sums of the stored values (caller zeroes it first)
 };
 
 int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st);
 
-// ld of a plane holding `cols` columns: rows must be 16-byte multiples for TMA
-inline int plane_ld(int cols) { return (cols + 3) / 4 * 4; }
+// ld of a plane holding `cols` columns: TMA needs 16-byte row multiples; rows padded to whole 128-byte lines make
+// every 128-byte box row exactly one L2 line (an unaligned 2000-byte pitch splits each into two requests)
+inline int plane_ld(int cols) { return (cols + 31) / 32 * 32; }
 
 // split a plain matrix into (hi, lo) planes (lo == nullptr: plain copy with the plane's ld)
 int tc_split_planes(const float* src, int ld_src, int rows, int cols, float* hi, float* lo, int ld_dst,

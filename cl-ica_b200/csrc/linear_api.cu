@@ -11,6 +11,7 @@
 // operand format ((hi, lo) planes in 3xTF32 mode) so that no conversion pass is ever needed.
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "skinny.cuh"
 
 namespace clica {
 
@@ -38,9 +39,61 @@ int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* d
 
 namespace {
 
+// ---- skinny-layer launchers (skinny.cuh) ----------------------------------------------------------------
+int launch_skinny_kin(const SkinnyKinParams& q, cudaStream_t st) {
+    const int grid = ceil_div(q.M, kSkRows);
+    LaunchScope ls(st, kFamGemmSimt);
+    if (q.K <= 16) skinny_kin_kernel<16><<<grid, 256, 0, st>>>(q);
+    else skinny_kin_kernel<48><<<grid, 256, 0, st>>>(q);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+bool skinny_nout_ok(int N, int K) { return N <= 48 && (size_t)N * K * sizeof(float) <= 96 * 1024; }
+int launch_skinny_nout(const SkinnyNoutParams& q, int sm_count, cudaStream_t st) {
+    const size_t smem = (size_t)q.N * q.K * sizeof(float);
+    int grid = ceil_div(q.M, 8);
+    if (grid > 8 * sm_count) grid = 8 * sm_count;
+    static bool attr = false;
+    if (!attr) {
+        CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    LaunchScope ls(st, kFamGemmSimt);
+    if (q.N <= 16) skinny_nout_kernel<16><<<grid, 256, smem, st>>>(q);
+    else skinny_nout_kernel<48><<<grid, 256, smem, st>>>(q);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+bool skinny_dw_ok(int N, int K) { return (size_t)kSkRows * (N + K + 1) * sizeof(float) <= 64 * 1024 && (size_t)N * (K + 1) <= 32768; }
+int launch_skinny_dw(const SkinnyDwParams& q, cudaStream_t st) {
+    const size_t smem = (size_t)kSkRows * (q.N + q.K + 1) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    LaunchScope ls(st, kFamGemmSimt);
+    skinny_dw_kernel<<<ceil_div(q.M, kSkRows), 256, smem, st>>>(q);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // y = act(x W^T + b); x, y given as (hi, lo) pairs (lo nullable)
 int simt_fwd(PlanesIn x, const float* W, int ldw, const float* b, PlanesOut y, int M, int K, int N, float slope,
-             cudaStream_t st) {
+             int sm_count, cudaStream_t st) {
+    if (K <= 48) {
+        SkinnyKinParams s = {};
+        s.x_hi = x.hi; s.x_lo = x.lo; s.ldx = x.ld; s.B = W; s.b_sk = 1; s.b_sn = ldw; s.bias = b; s.slope = slope;
+        s.o_hi = y.hi; s.o_lo = y.lo; s.ldo = y.ld; s.M = M; s.N = N; s.K = K; s.epi = 0;
+        return launch_skinny_kin(s, st);
+    }
+    if (y.lo == nullptr && skinny_nout_ok(N, K)) {
+        SkinnyNoutParams s = {};
+        s.x_hi = x.hi; s.x_lo = x.lo; s.ldx = x.ld; s.W = W; s.ldw = ldw; s.bias = b; s.out = y.hi; s.ldo = y.ld;
+        s.slope = slope; s.M = M; s.N = N; s.K = K;
+        return launch_skinny_nout(s, sm_count, st);
+    }
     SimtGemmParams q = {};
     q.A = x.hi; q.A_lo = x.lo; q.a_sm = x.ld; q.a_sk = 1;
     q.B = W; q.B_lo = nullptr; q.b_sk = 1; q.b_sn = ldw;
@@ -50,17 +103,32 @@ int simt_fwd(PlanesIn x, const float* W, int ldw, const float* b, PlanesOut y, i
 }
 // dx = (dy W) * mask(aux)
 int simt_bwd_data(PlanesIn dy, const float* W, int ldw, const float* aux, int ldaux, float slope_prev, PlanesOut dx,
-                  int M, int K, int N, cudaStream_t st) {
+                  int M, int K, int N, float* colsum, cudaStream_t st) {
+    if (N <= 48) {     // the reduction runs over the layer's (small) output width
+        SkinnyKinParams s = {};
+        s.x_hi = dy.hi; s.x_lo = dy.lo; s.ldx = dy.ld; s.B = W; s.b_sk = ldw; s.b_sn = 1; s.aux = aux; s.ldaux = ldaux;
+        s.slope = slope_prev; s.o_hi = dx.hi; s.o_lo = dx.lo; s.ldo = dx.ld; s.colsum = colsum;
+        s.M = M; s.N = K; s.K = N; s.epi = 1;
+        return launch_skinny_kin(s, st);
+    }
     SimtGemmParams q = {};
     q.A = dy.hi; q.A_lo = dy.lo; q.a_sm = dy.ld; q.a_sk = 1;      // [M x N], reduce over N
     q.B = W; q.B_lo = nullptr; q.b_sk = ldw; q.b_sn = 1;          // B(n, k) = W[n][k]
     q.C = dx.hi; q.C_lo = dx.lo; q.ldc = dx.ld; q.M = M; q.N = K; q.K = N; q.k_chunk = N;
-    q.aux = aux; q.ldaux = ldaux; q.slope = slope_prev; q.epilogue = kEpiMask;
+    q.aux = aux; q.ldaux = ldaux; q.slope = slope_prev; q.epilogue = kEpiMask; q.colsum = colsum;
     return simt_gemm(q, true, false, 1, st);
 }
 // dW = dy^T x (split-K over the M rows, atomics into the zeroed dW), db = column sums of dy
 int simt_bwd_weight(PlanesIn dy, PlanesIn x, float* dW, int lddw, float* db, int M, int K, int N, int sm_count,
                     cudaStream_t st) {
+    if (skinny_dw_ok(N, K)) {
+        CLICA_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
+        if (db) CLICA_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+        SkinnyDwParams s = {};
+        s.dy_hi = dy.hi; s.dy_lo = dy.lo; s.lddy = dy.ld; s.x_hi = x.hi; s.x_lo = x.lo; s.ldx = x.ld;
+        s.dW = dW; s.lddw = lddw; s.db = db; s.M = M; s.N = N; s.K = K;
+        return launch_skinny_dw(s, st);
+    }
     const int tiles = ceil_div(N, kSBM) * ceil_div(K, kSBN);
     int splits = (2 * sm_count + tiles - 1) / tiles;
     const int max_splits = ceil_div(M, 4 * kSBK);
@@ -178,7 +246,7 @@ extern "C" int clica_linear_act_fwd(const float* x, int ldx, const float* W, int
         CLICA_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(M, N, K, mode), CLICA_E_WORKSPACE, "linear_act_fwd: workspace too small");
         return tc_linear_fwd(x, ldx, W, ldw, b, y, ldy, M, K, N, slope, mode, ws, ws_bytes, di.sm_count, st);
     }
-    return simt_fwd(PlanesIn{x, nullptr, ldx}, W, ldw, b, PlanesOut{y, nullptr, ldy}, M, K, N, slope, st);
+    return simt_fwd(PlanesIn{x, nullptr, ldx}, W, ldw, b, PlanesOut{y, nullptr, ldy}, M, K, N, slope, di.sm_count, st);
 }
 
 extern "C" int clica_linear_act_bwd_data(const float* dy, int lddy, const float* W, int ldw,
@@ -198,7 +266,7 @@ extern "C" int clica_linear_act_bwd_data(const float* dy, int lddy, const float*
         return tc_linear_bwd_data(dy, lddy, W, ldw, x_act, ldxa, slope_prev, dx, lddx, M, K, N, mode, ws,
                                   ws_bytes, di.sm_count, st);
     }
-    return simt_bwd_data(PlanesIn{dy, nullptr, lddy}, W, ldw, x_act, ldxa, slope_prev, PlanesOut{dx, nullptr, lddx}, M, K, N, st);
+    return simt_bwd_data(PlanesIn{dy, nullptr, lddy}, W, ldw, x_act, ldxa, slope_prev, PlanesOut{dx, nullptr, lddx}, M, K, N, nullptr, st);
 }
 
 extern "C" int clica_linear_bwd_weight(const float* dy, int lddy, const float* x, int ldx,
@@ -257,7 +325,7 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
             g.Mo = M; g.No = N; g.Kr = K; g.epi = kTcBiasAct; g.bias = b[l]; g.slope = s; g.outp = y;
             rc = tc_gemm_launch(g, di.sm_count, st);
         } else {
-            rc = simt_fwd(x, W[l], K, b[l], y, M, K, N, s, st);
+            rc = simt_fwd(x, W[l], K, b[l], y, M, K, N, s, di.sm_count, st);
         }
         if (rc) return rc;
     }
@@ -280,6 +348,7 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
     if ((rc = pack_weights(p, w, W, st))) return rc;
 
     PlanesIn g = {g_out, nullptr, widths[L]};     // dL/d(pre-activation of layer l), starts as dL/d(output)
+    bool db_done = false;                         // db[l] already accumulated by the epilogue that produced g
     for (int l = L - 1; l >= 0; --l) {
         const int K = widths[l], N = widths[l + 1];
         PlanesIn x = act_in(p, acts, l);
@@ -290,12 +359,12 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
             t.A = g; t.a_mn_major = 1; t.B = x; t.b_mn_major = 1;
             t.Mo = N; t.No = K; t.Kr = M; t.epi = kTcAtomic; t.out = dW[l]; t.ldo = K; t.allow_split_k = 1;
             if ((rc = tc_gemm_launch(t, di.sm_count, st))) return rc;
-            if ((rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st))) return rc;
+            if (!db_done && (rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st))) return rc;
         } else {
-            if ((rc = simt_bwd_weight(g, x, dW[l], K, db[l], M, K, N, di.sm_count, st))) return rc;
+            if ((rc = simt_bwd_weight(g, x, dW[l], K, db_done ? nullptr : db[l], M, K, N, di.sm_count, st))) return rc;
         }
         if (l == 0) {
-            if (g_in) rc = simt_bwd_data(g, W[0], K, nullptr, 0, 1.f, PlanesOut{g_in, nullptr, K}, M, K, N, st);
+            if (g_in) rc = simt_bwd_data(g, W[0], K, nullptr, 0, 1.f, PlanesOut{g_in, nullptr, K}, M, K, N, nullptr, st);
             if (rc) return rc;
             break;
         }
@@ -304,15 +373,19 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
         gp.ld = p.act_ld(l);
         gp.hi = w.gbuf[l & 1];
         gp.lo = (p.nplanes == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
+        // the epilogue that writes g_prev also accumulates its column sums = db[l-1] (no separate reduction pass)
+        CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
         if (p.layer_tc(l)) {
             TcGemm t = {};
             t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1;
             t.Mo = M; t.No = K; t.Kr = N; t.epi = kTcMask; t.aux = x.hi; t.ldaux = x.ld; t.slope = slope; t.outp = gp;
+            t.colsum = db[l - 1];
             rc = tc_gemm_launch(t, di.sm_count, st);
         } else {
-            rc = simt_bwd_data(g, W[l], K, x.hi, x.ld, slope, gp, M, K, N, st);
+            rc = simt_bwd_data(g, W[l], K, x.hi, x.ld, slope, gp, M, K, N, db[l - 1], st);
         }
         if (rc) return rc;
+        db_done = true;
         g.hi = gp.hi; g.lo = gp.lo; g.ld = gp.ld;
     }
     return 0;
