@@ -99,8 +99,9 @@ class _ShardedInfoNCE(torch.autograd.Function):
         stats = stats / z_all.shape[0]
         ctx.save_for_backward(a_det, b_det, z_all, rowstat_all, pos)
         ctx.cfg = (p, tau, alpha, include_pos, rank * a_local.shape[0], ops)
-        ctx.mark_non_differentiable(loss_i)
-        return stats[0], loss_i, stats[1:].detach()
+        parts = stats[1:].clone()
+        ctx.mark_non_differentiable(loss_i, parts)
+        return stats[0], loss_i, parts
 
     @staticmethod
     def backward(ctx, g_mean, _g_li, _g_parts):
