@@ -181,6 +181,6 @@ static __global__ void __launch_bounds__(256) colsum_kernel(const float* __restr
 
 // host launchers (defined in linear_api.cu); operands given as (hi, lo) pairs with lo nullable
 int simt_gemm(const SimtGemmParams& q, bool a_kc, bool b_kc, int splits, cudaStream_t st);
-int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* db, cudaStream_t st);
+int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* db, cudaStream_t st, bool prezeroed = false);
 
 }  // namespace clica

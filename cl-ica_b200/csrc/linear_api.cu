@@ -26,8 +26,8 @@ int simt_gemm(const SimtGemmParams& q, bool a_kc, bool b_kc, int splits, cudaStr
     return 0;
 }
 
-int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* db, cudaStream_t st) {
-    CLICA_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* db, cudaStream_t st, bool prezeroed) {
+    if (!prezeroed) CLICA_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
     int ysplit = ceil_div(M, 256);
     if (ysplit > 64) ysplit = 64;
     const int rows_per_block = ceil_div(M, ysplit);
@@ -120,10 +120,12 @@ int simt_bwd_data(PlanesIn dy, const float* W, int ldw, const float* aux, int ld
 }
 // dW = dy^T x (split-K over the M rows, atomics into the zeroed dW), db = column sums of dy
 int simt_bwd_weight(PlanesIn dy, PlanesIn x, float* dW, int lddw, float* db, int M, int K, int N, int sm_count,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool prezeroed = false) {
     if (skinny_dw_ok(N, K)) {
-        CLICA_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
-        if (db) CLICA_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+        if (!prezeroed) {
+            CLICA_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
+            if (db) CLICA_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+        }
         SkinnyDwParams s = {};
         s.dy_hi = dy.hi; s.dy_lo = dy.lo; s.lddy = dy.ld; s.x_hi = x.hi; s.x_lo = x.lo; s.ldx = x.ld;
         s.dW = dW; s.lddw = lddw; s.db = db; s.M = M; s.N = N; s.K = K;
@@ -136,7 +138,7 @@ int simt_bwd_weight(PlanesIn dy, PlanesIn x, float* dW, int lddw, float* db, int
     if (splits < 1) splits = 1;
     const int chunk = ceil_div(ceil_div(M, splits), kSBK) * kSBK;
     splits = ceil_div(M, chunk);
-    CLICA_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
+    if (!prezeroed) CLICA_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), N, st));
     SimtGemmParams q = {};
     q.A = dy.hi; q.A_lo = dy.lo; q.a_sm = 1; q.a_sk = dy.ld;      // A(n, m) = dy[m][n]
     q.B = x.hi; q.B_lo = x.lo; q.b_sk = x.ld; q.b_sn = 1;         // B(m, k) = x[m][k]
@@ -144,7 +146,7 @@ int simt_bwd_weight(PlanesIn dy, PlanesIn x, float* dW, int lddw, float* db, int
     q.slope = 1.f; q.epilogue = kEpiAtomic;
     int rc = simt_gemm(q, false, false, splits, st);
     if (rc) return rc;
-    if (db) return simt_colsum(dy.hi, dy.lo, dy.ld, M, N, db, st);
+    if (db) return simt_colsum(dy.hi, dy.lo, dy.ld, M, N, db, st, prezeroed);
     return 0;
 }
 
@@ -162,12 +164,13 @@ struct MlpPlan {
     int L; const int* w; int M; int mode;
     int nplanes;                     // planes per hidden activation (2 in 3xTF32 mode, else 1)
     bool planar;                     // hidden activations use plane_ld() pitches
-    bool layer_tc(int l) const {
-        return tc_mode(mode) && l > 0 && l < L - 1 && tc_shape_ok(M, w[l + 1], w[l]);
+    bool layer_eligible(int l) const {      // M-independent: decides the packed-weight layout
+        return tc_mode(mode) && l > 0 && l < L - 1 && tc_shape_ok(32, w[l + 1], w[l]);
     }
+    bool layer_tc(int l) const { return layer_eligible(l) && tc_shape_ok(M, w[l + 1], w[l]); }
     int act_ld(int l) const { return planar ? plane_ld(w[l]) : w[l]; }
     size_t act_floats(int l) const { return (size_t)nplanes * M * act_ld(l); }
-    size_t wplane_floats(int l) const { return layer_tc(l) ? (size_t)nplanes * w[l + 1] * plane_ld(w[l]) : 0; }
+    size_t wplane_floats(int l) const { return layer_eligible(l) ? (size_t)nplanes * w[l + 1] * plane_ld(w[l]) : 0; }
 };
 MlpPlan make_plan(int L, const int* widths, int M, int mode) {
     MlpPlan p;
@@ -186,17 +189,20 @@ PlanesIn act_in(const MlpPlan& p, const float* const* acts, int l) {
 }
 PlanesOut as_out(PlanesIn a) { PlanesOut o; o.hi = (float*)a.hi; o.lo = (float*)a.lo; o.ld = a.ld; return o; }
 
-struct MlpWs { float* wplanes[64]; float* gbuf[2]; size_t bytes; };
-MlpWs carve_mlp(const MlpPlan& p, void* ws) {
+struct MlpWs { float* wplanes[64]; float* gbuf[2]; size_t bytes; size_t packed_bytes; };
+// `packed` (nullable): caller-provided packed weight planes (clica_mlp_pack_weights); otherwise they live in ws
+MlpWs carve_mlp(const MlpPlan& p, void* ws, const float* packed = nullptr) {
     MlpWs w;
     char* base = (char*)ws;
-    size_t off = 0;
+    size_t off = 0, woff = 0;
     size_t gmax = 0;
     for (int l = 0; l < p.L && l < 64; ++l) {
-        w.wplanes[l] = (float*)(base + off);
-        off += align_up(p.wplane_floats(l) * sizeof(float), 1024);
+        w.wplanes[l] = packed ? (float*)((char*)packed + woff) : (float*)(base + woff);
+        woff += align_up(p.wplane_floats(l) * sizeof(float), 1024);
         if (l > 0 && p.act_floats(l) > gmax) gmax = p.act_floats(l);
     }
+    w.packed_bytes = woff;
+    off = woff;          // (the region stays reserved in ws either way: one size formula for every caller)
     for (int k = 0; k < 2; ++k) {
         w.gbuf[k] = (float*)(base + off);
         off += align_up(gmax * sizeof(float), 1024);
@@ -213,7 +219,7 @@ PlanesIn weight_planes(const MlpPlan& p, const MlpWs& w, int l) {
 }
 int pack_weights(const MlpPlan& p, const MlpWs& w, const float* const* W, cudaStream_t st) {
     for (int l = 0; l < p.L; ++l) {
-        if (!p.layer_tc(l)) continue;
+        if (!p.layer_eligible(l)) continue;
         PlanesIn wp = weight_planes(p, w, l);
         int rc = tc_split_planes(W[l], p.w[l], p.w[l + 1], p.w[l], (float*)wp.hi, (float*)wp.lo, wp.ld, st);
         if (rc) return rc;
@@ -300,8 +306,26 @@ extern "C" size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int
     return carve_mlp(p, nullptr).bytes + 1024;
 }
 
+extern "C" size_t clica_mlp_packed_weight_bytes(int L, const int* widths, int mode) {
+    if (L < 1 || L > 64 || !widths) return 0;
+    MlpPlan p = make_plan(L, widths, 32, mode);
+    return carve_mlp(p, nullptr).packed_bytes + 1024;
+}
+
+extern "C" int clica_mlp_pack_weights(int L, const int* widths, const float* const* W, int mode, void* packed,
+                                      size_t packed_bytes, void* stream) {
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    CLICA_REQUIRE(L >= 1 && L <= 64 && widths && W && packed, CLICA_E_BADARG, "mlp_pack_weights: bad arguments");
+    CLICA_REQUIRE((((uintptr_t)packed) & 1023u) == 0, CLICA_E_ALIGN, "mlp_pack_weights: buffer must be 1024-byte aligned");
+    MlpPlan p = make_plan(L, widths, 32, mode);
+    MlpWs w = carve_mlp(p, nullptr, (const float*)packed);
+    CLICA_REQUIRE(packed_bytes >= w.packed_bytes, CLICA_E_WORKSPACE, "mlp_pack_weights: buffer %zu < %zu bytes", packed_bytes, w.packed_bytes);
+    return pack_weights(p, w, W, (cudaStream_t)stream);
+}
+
 extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, const float* const* b,
-                             float* const* acts, int M, float slope, int mode,
+                             float* const* acts, int M, float slope, int mode, const void* packed_weights,
                              void* ws, size_t ws_bytes, void* stream) {
     int rc = check_mode(mode);
     if (rc) return rc;
@@ -311,9 +335,9 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
     cudaStream_t st = (cudaStream_t)stream;
     MlpPlan p = make_plan(L, widths, M, mode);
     void* wsa = (void*)align_up((size_t)(uintptr_t)ws, 1024);
-    MlpWs w = carve_mlp(p, wsa);
+    MlpWs w = carve_mlp(p, wsa, (const float*)packed_weights);
     CLICA_REQUIRE(ws && ws_bytes >= w.bytes + 1024, CLICA_E_WORKSPACE, "mlp_fwd: workspace %zu < %zu bytes", ws_bytes, w.bytes + 1024);
-    if ((rc = pack_weights(p, w, W, st))) return rc;
+    if (!packed_weights && (rc = pack_weights(p, w, W, st))) return rc;
     for (int l = 0; l < L; ++l) {
         const int K = widths[l], N = widths[l + 1];
         const float s = (l == L - 1) ? 1.f : slope;
@@ -334,7 +358,8 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
 
 extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, const float* const* acts,
                              const float* g_out, float* const* dW, float* const* db, float* g_in,
-                             int M, float slope, int mode, void* ws, size_t ws_bytes, void* stream) {
+                             int M, float slope, int mode, const void* packed_weights, int grads_prezeroed,
+                             void* ws, size_t ws_bytes, void* stream) {
     int rc = check_mode(mode);
     if (rc) return rc;
     CLICA_REQUIRE(L >= 1 && L <= 64 && widths && W && acts && g_out && dW && db && M >= 1, CLICA_E_BADARG, "mlp_bwd: bad arguments");
@@ -343,9 +368,10 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
     cudaStream_t st = (cudaStream_t)stream;
     MlpPlan p = make_plan(L, widths, M, mode);
     void* wsa = (void*)align_up((size_t)(uintptr_t)ws, 1024);
-    MlpWs w = carve_mlp(p, wsa);
+    MlpWs w = carve_mlp(p, wsa, (const float*)packed_weights);
     CLICA_REQUIRE(ws && ws_bytes >= w.bytes + 1024, CLICA_E_WORKSPACE, "mlp_bwd: workspace %zu < %zu bytes", ws_bytes, w.bytes + 1024);
-    if ((rc = pack_weights(p, w, W, st))) return rc;
+    if (!packed_weights && (rc = pack_weights(p, w, W, st))) return rc;
+    const bool pz = grads_prezeroed != 0;
 
     PlanesIn g = {g_out, nullptr, widths[L]};     // dL/d(pre-activation of layer l), starts as dL/d(output)
     bool db_done = false;                         // db[l] already accumulated by the epilogue that produced g
@@ -354,14 +380,14 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
         PlanesIn x = act_in(p, acts, l);
         // dW[l] = g^T x ; db[l] = column sums of g
         if (p.layer_tc(l)) {
-            CLICA_CUDA_OK(cudaMemsetAsync(dW[l], 0, (size_t)N * K * sizeof(float), st));
+            if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(dW[l], 0, (size_t)N * K * sizeof(float), st));
             TcGemm t = {};
             t.A = g; t.a_mn_major = 1; t.B = x; t.b_mn_major = 1;
             t.Mo = N; t.No = K; t.Kr = M; t.epi = kTcAtomic; t.out = dW[l]; t.ldo = K; t.allow_split_k = 1;
             if ((rc = tc_gemm_launch(t, di.sm_count, st))) return rc;
-            if (!db_done && (rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st))) return rc;
+            if (!db_done && (rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st, pz))) return rc;
         } else {
-            if ((rc = simt_bwd_weight(g, x, dW[l], K, db_done ? nullptr : db[l], M, K, N, di.sm_count, st))) return rc;
+            if ((rc = simt_bwd_weight(g, x, dW[l], K, db_done ? nullptr : db[l], M, K, N, di.sm_count, st, pz))) return rc;
         }
         if (l == 0) {
             if (g_in) rc = simt_bwd_data(g, W[0], K, nullptr, 0, 1.f, PlanesOut{g_in, nullptr, K}, M, K, N, nullptr, st);
@@ -374,7 +400,7 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
         gp.hi = w.gbuf[l & 1];
         gp.lo = (p.nplanes == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
         // the epilogue that writes g_prev also accumulates its column sums = db[l-1] (no separate reduction pass)
-        CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
+        if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
         if (p.layer_tc(l)) {
             TcGemm t = {};
             t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1;

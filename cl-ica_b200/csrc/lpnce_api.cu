@@ -175,19 +175,38 @@ SplitPlan plan_splits(int rows, int rows_cta, int MS, int sm_count, int ctas_per
     pl.nsplit = ceil_div(col_tiles, pl.tiles_per_split);
     return pl;
 }
-// register-limited occupancy estimate, used only to size the grid (any value is correct)
-int ctas_per_sm_guess(int DP, int R, bool bwd) {
-    const int regs = (bwd ? 4 : 2) * DP * R + 4 * DP + 40;
-    int n = 65536 / (kThreads * (regs > 32 ? regs : 32));
-    return n < 1 ? 1 : (n > 4 ? 4 : n);
+// resident CTAs per SM of the kernel that will run (cudaOccupancy..., cached per instantiation)
+int occ_fwd(int pc, int DP) {
+    int n;
+    switch (pc) {
+        case 1: n = occ_fwd_p1(DP); break;
+        case 2: n = occ_fwd_p2(DP); break;
+        case 3: n = occ_fwd_p3(DP); break;
+        case 4: n = occ_fwd_p4(DP); break;
+        default: n = occ_fwd_p0(DP); break;
+    }
+    return n < 1 ? 1 : n;
 }
+int occ_bwd(int pc, int DP) {
+    int n;
+    switch (pc) {
+        case 1: n = occ_bwd_p1(DP); break;
+        case 2: n = occ_bwd_p2(DP); break;
+        case 3: n = occ_bwd_p3(DP); break;
+        case 4: n = occ_bwd_p4(DP); break;
+        default: n = occ_bwd_p0(DP); break;
+    }
+    return n < 1 ? 1 : n;
+}
+// The split plan only depends on (rows, MS, DP, #SMs) -- NOT on the exponent -- so that the workspace queries
+// (which do not know p) and the launches agree: the most common occupancy of the family is used (p = 2).
 SplitPlan plan_fwd(int B, int M, int DP, int sms) {
     const int R = fwd_rows_per_thread(DP);
-    return plan_splits(B, rows_per_cta(R), M, sms, ctas_per_sm_guess(DP, R, false));
+    return plan_splits(B, rows_per_cta(R), M, sms, occ_fwd(2, DP));
 }
 SplitPlan plan_bwd(int rows, int MS, int DP, int sms) {
     const int R = bwd_rows_per_thread(DP);
-    return plan_splits(rows, rows_per_cta(R), MS, sms, ctas_per_sm_guess(DP, R, true));
+    return plan_splits(rows, rows_per_cta(R), MS, sms, occ_bwd(2, DP));
 }
 
 int dispatch_fwd(int pc, int DP, const FwdParams& q, dim3 g, cudaStream_t s) {
@@ -345,7 +364,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         if (needA) {   // anchors own, negatives stream
             BwdRole& r = q.role[q.nroles++];
             r.O = z1; r.ldO = ld1; r.BO = B; r.S = z3; r.ldS = ld3; r.MS = M;
-            r.LO = (const float2*)rowstat; r.LS = nullptr; r.ES = nullptr;
+            r.LO = (const float2*)rowstat; r.LS = nullptr; r.ES = nullptr; r.EO = nullptr;
             r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z3, ld3, d, DP);
             r.part = w.partA; r.part_rows = B; r.row_tiles = pa.row_tiles;
             gx = max(gx, pa.row_tiles); gy = max(gy, pa.nsplit);
@@ -353,7 +372,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         if (needB) {   // negatives own, anchors (with their lse and coefficient) stream
             BwdRole& r = q.role[q.nroles++];
             r.O = z3; r.ldO = ld3; r.BO = M; r.S = z1; r.ldS = ld1; r.MS = B;
-            r.LO = nullptr; r.LS = (const float2*)rowstat; r.ES = w.E;
+            r.LO = nullptr; r.LS = (const float2*)rowstat; r.ES = w.E; r.EO = nullptr;
             r.tiles_per_split = pb.tiles_per_split; r.nsplit = pb.nsplit; r.flat16 = is_flat16(z1, ld1, d, DP);
             r.part = w.partB; r.part_rows = M; r.row_tiles = pb.row_tiles;
             gx = max(gx, pb.row_tiles); gy = max(gy, pb.nsplit);
@@ -430,24 +449,24 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp); }
     CLICA_CUDA_OK(cudaGetLastError());
 
+    // ONE merged pass: the local rows are owners, every global row streams by once; the pair (i, j) contributes
+    // [E_i w(i->j) + E_j w(j->i)] G'(z_j - z_i) -- anchor role and column role share the (symmetric) distance.
     BwdParams q;
-    q.d = d; q.coef = kLog2e / tau; q.pg = p; q.nroles = 2;
-    const int flat = is_flat16(z_all, ld3, d, DP);
-    for (int k = 0; k < 2; ++k) {
-        BwdRole& r = q.role[k];
+    q.d = d; q.coef = kLog2e / tau; q.pg = p; q.nroles = 1;
+    {
+        BwdRole& r = q.role[0];
         r.O = z1_local; r.ldO = ld1; r.BO = B; r.S = z_all; r.ldS = ld3; r.MS = M;
-        r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = flat;
+        r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z_all, ld3, d, DP);
         r.part_rows = B; r.row_tiles = pa.row_tiles;
+        r.LO = stat_all + row0; r.EO = w.E + row0; r.LS = stat_all; r.ES = w.E; r.part = w.partB;
     }
-    q.role[0].LO = stat_all + row0; q.role[0].LS = nullptr; q.role[0].ES = nullptr; q.role[0].part = w.partA;   // local rows as anchors
-    q.role[1].LO = nullptr; q.role[1].LS = stat_all; q.role[1].ES = w.E; q.role[1].part = w.partB;             // local rows as negatives
-    { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 2), st); }
+    { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 1), st); }
     if (rc) return rc;
 
     ReduceParams r;
-    r.partA = w.partA; r.nsA = pa.nsplit; r.rowsA = B;
+    r.partA = nullptr; r.nsA = 0; r.rowsA = 0;
     r.partB = w.partB; r.nsB = pa.nsplit; r.rowsB = B;
-    r.E = w.E + row0; r.CP = w.CP; r.z1 = z1_local; r.ld1 = ld1; r.z2 = z2_local; r.ld2 = ld2;
+    r.E = nullptr; r.CP = w.CP; r.z1 = z1_local; r.ld1 = ld1; r.z2 = z2_local; r.ld2 = ld2;
     r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
     r.rows = B; r.d = d; r.TW = TW; r.p = p;
     const long long n = (long long)B * d;

@@ -12,4 +12,10 @@ int CLICA_CAT(launch_fwd_p, CLICA_P)(int DP, const FwdParams& q, dim3 g, cudaStr
 int CLICA_CAT(launch_bwd_p, CLICA_P)(int DP, const BwdParams& q, dim3 g, cudaStream_t s) {
     CLICA_DISPATCH_DP(CLICA_P, DP, launch_bwd_pd, q, g, s)
 }
+int CLICA_CAT(occ_fwd_p, CLICA_P)(int DP) {
+    CLICA_DISPATCH_DP(CLICA_P, DP, occ_fwd_pd)
+}
+int CLICA_CAT(occ_bwd_p, CLICA_P)(int DP) {
+    CLICA_DISPATCH_DP(CLICA_P, DP, occ_bwd_pd)
+}
 }  // namespace clica

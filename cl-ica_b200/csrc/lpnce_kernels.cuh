@@ -64,6 +64,9 @@ struct BwdRole {
     const float* S; int ldS; int MS;
     const float2* LO;                   // owner row statistics (nullable -> (0, 0))
     const float2* LS; const float* ES;  // streamed row statistics and coefficient (both or neither)
+    const float* EO;                    // MERGED mode (owner set == streamed set, e.g. z3 = roll(z1)): owner coefficient;
+                                        // distance is symmetric, so one pass accumulates both roles:
+                                        // w = EO[i] exp2(.. - stat_i) + ES[j] exp2(.. - stat_j)
     int tiles_per_split; int nsplit; int flat16;
     float* part; int part_rows;        // [nsplit][part_rows][2*DP]
     int row_tiles;
@@ -245,12 +248,14 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
                 float x0 = fmaf(D0, -q.coef, -m[r]);
                 float x1 = fmaf(D1, -q.coef, -m[r]);
                 const float hi = fmaxf(x0, x1);
-                if (hi > kRescale) {   // rare: a much closer negative than the reference point appeared
-                    const float mn = m[r] + hi;
-                    s[r] *= ex2_approx(m[r] - mn);
-                    m[r] = mn;
-                    x0 = fmaf(D0, -q.coef, -mn);
-                    x1 = fmaf(D1, -q.coef, -mn);
+                if (__any_sync(0xffffffffu, hi > kRescale)) {   // warp-uniform branch; rare: a much closer negative
+                    if (hi > kRescale) {                        // than the reference point appeared
+                        const float mn = m[r] + hi;
+                        s[r] *= ex2_approx(m[r] - mn);
+                        m[r] = mn;
+                        x0 = fmaf(D0, -q.coef, -mn);
+                        x1 = fmaf(D1, -q.coef, -mn);
+                    }
                 }
                 s[r] += ex2_approx(x0) + ex2_approx(x1);
             }
@@ -306,7 +311,8 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
 
     float2 na[R][DP];
     float2 gacc[R][DP];
-    float lo_m[R], lo_s[R];
+    float lo_m[R], lo_s[R], eo[R];
+    const bool merged = (ro.EO != nullptr);
     load_owner_rows<DP, R>(na, ro.O, ro.ldO, ro.BO, q.d, row_base, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -315,6 +321,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         for (int c = 0; c < DP; ++c) gacc[r][c] = make_float2(0.f, 0.f);
         const float2 st = (ro.LO != nullptr && row < ro.BO) ? __ldg(ro.LO + row) : make_float2(0.f, 0.f);
         lo_m[r] = st.x; lo_s[r] = st.y;
+        eo[r] = (merged && row < ro.BO) ? __ldg(ro.EO + row) : 0.f;
     }
 
     const int ntiles = (ro.MS + kTN - 1) / kTN;
@@ -370,9 +377,16 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
                     a0 = Lp<P>::accum(__fadd2_rn(bb[c], na[r][c]), a0, q.pg);
                     a1 = Lp<P>::accum(__fadd2_rn(bb[DP + c], na[r][c]), a1, q.pg);
                 }
-                // exactly one of (owner, streamed) statistics is non-zero; m2 is subtracted inside the fma
-                const float w0 = es0 * ex2_approx(fmaf(a0.x + a0.y, -q.coef, -(lo_m[r] + sm0)) - (lo_s[r] + sl0));
-                const float w1 = es1 * ex2_approx(fmaf(a1.x + a1.y, -q.coef, -(lo_m[r] + sm1)) - (lo_s[r] + sl1));
+                float w0, w1;
+                const float D0 = a0.x + a0.y, D1 = a1.x + a1.y;
+                if (merged) {   // both roles at once (warp-uniform branch); m2 is subtracted inside the fma
+                    w0 = eo[r] * ex2_approx(fmaf(D0, -q.coef, -lo_m[r]) - lo_s[r]) + es0 * ex2_approx(fmaf(D0, -q.coef, -sm0) - sl0);
+                    w1 = eo[r] * ex2_approx(fmaf(D1, -q.coef, -lo_m[r]) - lo_s[r]) + es1 * ex2_approx(fmaf(D1, -q.coef, -sm1) - sl1);
+                    if (!has1) w1 = 0.f;
+                } else {        // exactly one of (owner, streamed) statistics is non-zero
+                    w0 = es0 * ex2_approx(fmaf(D0, -q.coef, -(lo_m[r] + sm0)) - (lo_s[r] + sl0));
+                    w1 = es1 * ex2_approx(fmaf(D1, -q.coef, -(lo_m[r] + sm1)) - (lo_s[r] + sl1));
+                }
 #pragma unroll
                 for (int c = 0; c < DP; ++c) {
                     gacc[r][c] = Lp<P>::grad(w0, __fadd2_rn(bb[c], na[r][c]), gacc[r][c], q.pg);
@@ -436,6 +450,30 @@ int launch_bwd_pd(const BwdParams& q, dim3 grid, cudaStream_t st) {
     return 0;
 }
 
+// resident CTAs per SM of one instantiation (sizes the grid: splits are chosen so that the CTAs fill whole waves)
+template <int P, int DP>
+int occ_fwd_pd() {
+    static int cached = 0;
+    if (cached == 0) {
+        constexpr int R = fwd_rows_per_thread(DP);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_fwd_kernel<P, DP, R, kCW>, kThreads, fwd_smem_bytes(DP, R)) != cudaSuccess) n = 1;
+        cached = n < 1 ? 1 : n;
+    }
+    return cached;
+}
+template <int P, int DP>
+int occ_bwd_pd() {
+    static int cached = 0;
+    if (cached == 0) {
+        constexpr int R = bwd_rows_per_thread(DP);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_bwd_kernel<P, DP, R, kCW>, kThreads, bwd_smem_bytes(DP, R)) != cudaSuccess) n = 1;
+        cached = n < 1 ? 1 : n;
+    }
+    return cached;
+}
+
 #define CLICA_DISPATCH_DP(P_, DPV, FN, ...)                                                \
     switch (DPV) {                                                                         \
         case 2: return FN<P_, 2>(__VA_ARGS__);                                             \
@@ -462,5 +500,7 @@ int launch_bwd_p1(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p2(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p3(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p4(int DP, const BwdParams& q, dim3 g, cudaStream_t s);
+int occ_fwd_p0(int DP); int occ_fwd_p1(int DP); int occ_fwd_p2(int DP); int occ_fwd_p3(int DP); int occ_fwd_p4(int DP);
+int occ_bwd_p0(int DP); int occ_bwd_p1(int DP); int occ_bwd_p2(int DP); int occ_bwd_p3(int DP); int occ_bwd_p4(int DP);
 
 }  // namespace clica

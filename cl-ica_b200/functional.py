@@ -62,7 +62,7 @@ def _ptr(t: Optional[torch.Tensor]):
 # ---- fused Lp-InfoNCE loss ----------------------------------------------------------------------------
 class _LpInfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z1, z2, z3, p, tau, alpha, include_pos):
+    def forward(ctx, z1, z2, z3, p, tau, alpha, include_pos, symmetric=False):
         lib = _lib.load()
         z1, z2, z3 = _as_rows(z1, "z1_rec"), _as_rows(z2, "z2_con_z1_rec"), _as_rows(z3, "z3_rec")
         B, d = z1.shape
@@ -83,6 +83,7 @@ class _LpInfoNCE(torch.autograd.Function):
             _lib.check(rc, "clica_lpnce_fwd")
         ctx.save_for_backward(z1, z2, z3, rowstat, pos)
         ctx.cfg = (float(p), float(tau), float(alpha), int(include_pos))
+        ctx.symmetric = bool(symmetric) and z3.shape[0] == B
         ctx.set_materialize_grads(False)
         mean, pos_mean, neg_mean = scal[0], scal[1], scal[2]
         ctx.mark_non_differentiable(pos_mean, neg_mean)
@@ -98,7 +99,23 @@ class _LpInfoNCE(torch.autograd.Function):
         dev = z1.device
         need1, need2, need3 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         if not (need1 or need2 or need3) or (g_mean is None and g_loss_i is None):
-            return (None,) * 7
+            return (None,) * 8
+        if ctx.symmetric and g_loss_i is None:
+            # z3 is a row permutation of z1 (torch.roll, main_mlp.py:272): the pair distance is symmetric, so the
+            # anchor-role and the column-role gradients come out of ONE merged pass (clica_lpnce_bwd_sharded with
+            # the whole batch as the local shard); the roll's own backward then receives no gradient for z3.
+            with torch.cuda.device(dev):
+                g1 = torch.empty((B, d), dtype=torch.float32, device=dev)
+                g2 = torch.empty((B, d), dtype=torch.float32, device=dev)
+                g_mean = g_mean.to(device=dev, dtype=torch.float32).contiguous()
+                nbytes = lib.clica_lpnce_bwd_sharded_workspace_bytes(B, B, d)
+                ws = _workspace(nbytes, dev, "lpnce_bwd")
+                rc = lib.clica_lpnce_bwd_sharded(z1.data_ptr(), _ld(z1), z2.data_ptr(), _ld(z2), z1.data_ptr(), _ld(z1),
+                                                 rowstat.data_ptr(), pos.data_ptr(), B, B, d, 0, p, tau, alpha,
+                                                 include_pos, g_mean.data_ptr(), g1.data_ptr(), d, g2.data_ptr(), d,
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                _lib.check(rc, "clica_lpnce_bwd_sharded")
+            return g1 if need1 else None, g2 if need2 else None, None, None, None, None, None, None
         with torch.cuda.device(dev):
             g1 = torch.empty_like(z1, memory_format=torch.contiguous_format) if need1 else None
             g2 = torch.empty_like(z2, memory_format=torch.contiguous_format) if need2 else None
@@ -114,12 +131,34 @@ class _LpInfoNCE(torch.autograd.Function):
                                      _ptr(g_mean), _ptr(g_loss_i), _ptr(g1), d, _ptr(g2), d, _ptr(g3), d,
                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_lpnce_bwd")
-        return g1, g2, g3, None, None, None, None
+        return g1, g2, g3, None, None, None, None, None
 
 
-def lp_infonce(z1_rec, z2_rec, z3_rec, p, tau=1.0, alpha=0.5, include_pos=True):
-    """Fused Lp-InfoNCE. Returns ``(mean, per_item[B], pos_mean, neg_mean)``; mean and per_item carry grad."""
-    return _LpInfoNCE.apply(z1_rec, z2_rec, z3_rec, p, tau, alpha, include_pos)
+def is_row_roll_of(z3, z1) -> bool:
+    """True when autograd itself says ``z3 = torch.roll(z1, k, 0)`` (the reference's negatives, main_mlp.py:272)."""
+    fn = getattr(z3, "grad_fn", None)
+    if fn is None or type(fn).__name__ != "RollBackward0" or z1.dim() != 2 or z3.shape != z1.shape:
+        return False
+    try:
+        dims = tuple(int(x) for x in fn._saved_dims)
+        src, out_nr = fn.next_functions[0]
+    except Exception:
+        return False
+    if dims not in ((0,), (-2,)):
+        return False
+    if z1.grad_fn is not None:
+        return src is z1.grad_fn and out_nr == z1.output_nr
+    return getattr(src, "variable", None) is z1
+
+
+def lp_infonce(z1_rec, z2_rec, z3_rec, p, tau=1.0, alpha=0.5, include_pos=True, symmetric=None):
+    """Fused Lp-InfoNCE. Returns ``(mean, per_item[B], pos_mean, neg_mean)``; mean and per_item carry grad.
+
+    ``symmetric`` (default: detected from the autograd graph) declares that ``z3_rec`` is a row permutation of
+    ``z1_rec``; the backward then needs a single pass over the B x B pairs instead of two."""
+    if symmetric is None:
+        symmetric = is_row_roll_of(z3_rec, z1_rec)
+    return _LpInfoNCE.apply(z1_rec, z2_rec, z3_rec, p, tau, alpha, include_pos, bool(symmetric))
 
 
 # ---- encoder stack ------------------------------------------------------------------------------------
@@ -128,6 +167,33 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()
     return arr
+
+
+# packed (GEMM-operand-format) copies of the encoder weights, keyed by the first weight's storage; refreshed whenever
+# any weight's version counter moves (i.e. once per optimizer step, while the encoder runs four times per step)
+_packed_cache = {}
+
+
+def _packed_weights(lib, Ws, widths, mode, dev) -> int:
+    """Device pointer (1024-byte aligned) of the packed weight planes, re-packed only when a weight changed."""
+    key = (dev.index, Ws[0].data_ptr(), int(mode))
+    sig = tuple((W.data_ptr(), W._version) for W in Ws)
+    stream = _stream_ptr(dev)
+    hit = _packed_cache.get(key)
+    if hit is not None and hit[0] == sig and hit[2] == stream:
+        return hit[3]
+    L = len(Ws)
+    cw = (ctypes.c_int * (L + 1))(*widths)
+    nbytes = lib.clica_mlp_packed_weight_bytes(L, cw, int(mode))
+    if hit is not None and hit[1].numel() >= nbytes + 1024 and hit[2] == stream:
+        buf = hit[1]
+    else:
+        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)     # the allocator only guarantees 512 B
+    ptr = (buf.data_ptr() + 1023) // 1024 * 1024
+    rc = lib.clica_mlp_pack_weights(L, cw, _ptr_array(Ws), int(mode), ptr, nbytes, stream)
+    _lib.check(rc, "clica_mlp_pack_weights")
+    _packed_cache[key] = (sig, buf, stream, ptr)
+    return ptr
 
 
 class _MLP(torch.autograd.Function):
@@ -159,8 +225,9 @@ class _MLP(torch.autograd.Function):
             cw = (ctypes.c_int * (L + 1))(*widths)
             nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
             ws = _workspace(nbytes, dev, "mlp")
+            packed = _packed_weights(lib, Ws, widths, mode, dev)
             rc = lib.clica_mlp_fwd(L, cw, _ptr_array(Ws), _ptr_array(bs), _ptr_array(acts), M, float(slope),
-                                   int(mode), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                                   int(mode), packed, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_mlp_fwd")
         ctx.save_for_backward(*acts[:-1], *Ws)
         ctx.cfg = (L, widths, float(slope), int(mode), [b is not None for b in bs])
@@ -176,15 +243,23 @@ class _MLP(torch.autograd.Function):
         dev = gy.device
         gy = gy.contiguous()
         with torch.cuda.device(dev):
-            dWs = [torch.empty_like(W) for W in Ws]
-            dbs = [torch.empty(W.shape[0], dtype=torch.float32, device=dev) for W in Ws]
+            # all parameter gradients live in ONE zero-initialised flat buffer (split-K / fused column sums accumulate)
+            sizes = [W.numel() for W in Ws] + [W.shape[0] for W in Ws]
+            offs, tot = [], 0
+            for n_el in sizes:
+                offs.append(tot)
+                tot += (n_el + 3) // 4 * 4                     # keep every tensor 16-byte aligned
+            flat = torch.zeros(tot, dtype=torch.float32, device=dev)
+            dWs = [flat[offs[l]:offs[l] + sizes[l]].view_as(Ws[l]) for l in range(L)]
+            dbs = [flat[offs[L + l]:offs[L + l] + sizes[L + l]] for l in range(L)]
             g_in = torch.empty_like(acts[0]) if ctx.needs_input_grad[0] else None
             cw = (ctypes.c_int * (L + 1))(*widths)
             nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
             ws = _workspace(nbytes, dev, "mlp")
+            packed = _packed_weights(lib, Ws, widths, mode, dev)
             rc = lib.clica_mlp_bwd(L, cw, _ptr_array(Ws), _ptr_array(acts), gy.data_ptr(), _ptr_array(dWs),
-                                   _ptr_array(dbs), _ptr(g_in), M, slope, mode, ws.data_ptr(), ws.numel(),
-                                   _stream_ptr(dev))
+                                   _ptr_array(dbs), _ptr(g_in), M, slope, mode, packed, 1,
+                                   ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_mlp_bwd")
         grads = []
         for l in range(L):

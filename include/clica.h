@@ -171,13 +171,22 @@ CLICA_API int clica_linear_bwd_weight(const float* dy, int lddy, const float* x,
 CLICA_API size_t clica_mlp_act_floats(int M, int width, int mode);
 CLICA_API size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode);
 
+/* Weights change once per optimizer step but the encoder runs four times per step (2 forward, 2 backward):
+ * clica_mlp_pack_weights converts them once into the GEMM operand format (`packed`: 1024-byte aligned,
+ * clica_mlp_packed_weight_bytes bytes) and fwd / bwd take it as `packed_weights` (NULL: packed internally).
+ * grads_prezeroed != 0: the caller has already zeroed every dW[l] / db[l] (one memset of a flat buffer). */
+CLICA_API size_t clica_mlp_packed_weight_bytes(int L, const int* widths, int mode);
+CLICA_API int clica_mlp_pack_weights(int L, const int* widths, const float* const* W, int mode, void* packed,
+                  size_t packed_bytes, void* stream);
+
 CLICA_API int clica_mlp_fwd(int L, const int* widths, const float* const* W, const float* const* b,
-                  float* const* acts, int M, float slope, int mode,
+                  float* const* acts, int M, float slope, int mode, const void* packed_weights,
                   void* ws, size_t ws_bytes, void* stream);
 
 CLICA_API int clica_mlp_bwd(int L, const int* widths, const float* const* W, const float* const* acts,
                   const float* g_out, float* const* dW, float* const* db, float* g_in,
-                  int M, float slope, int mode, void* ws, size_t ws_bytes, void* stream);
+                  int M, float slope, int mode, const void* packed_weights, int grads_prezeroed,
+                  void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam step.     replaces  torch.optim.Adam.step (main_mlp.py:283,312) for the
