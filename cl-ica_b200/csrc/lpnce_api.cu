@@ -148,12 +148,18 @@ __global__ void lpnce_reduce_kernel(const ReduceParams q) {
 }
 
 // ---- host-side planning ---------------------------------------------------------------------------
+// feature pairs per lane (DP) and lanes per pair (F): d <= 40 is held by one lane; wider d is split over
+// F in {2, 4, 8} adjacent lanes with DP in {16, 20} (d <= 320)
+struct Shape { int DP; int F; };
 const int kDpList[] = {2, 3, 4, 5, 8, 12, 16, 20};
-int pick_dp(int d) {
+Shape pick_shape(int d) {
     const int need = (d + 1) / 2;
-    for (int v : kDpList) if (v >= need) return v;
-    return -1;
+    for (int v : kDpList) if (v >= need) return Shape{v, 1};
+    for (int f = 2; f <= 8; f *= 2)
+        for (int v : {16, 20}) if (v * f >= need) return Shape{v, f};
+    return Shape{-1, 0};
 }
+int pick_dp(int d) { return pick_shape(d).DP; }
 int p_code(float p) {
     if (p == 1.f) return 1;
     if (p == 2.f) return 2;
@@ -163,10 +169,10 @@ int p_code(float p) {
 }
 
 struct SplitPlan { int row_tiles; int tiles_per_split; int nsplit; };
-SplitPlan plan_splits(int rows, int rows_cta, int MS, int sm_count, int ctas_per_sm) {
+SplitPlan plan_splits(int rows, int rows_cta, int MS, int tile_cols, int sm_count, int ctas_per_sm) {
     SplitPlan pl;
     pl.row_tiles = ceil_div(rows, rows_cta);
-    const int col_tiles = ceil_div(MS, kTN);
+    const int col_tiles = ceil_div(MS, tile_cols);
     int want = (sm_count * ctas_per_sm) / (pl.row_tiles > 0 ? pl.row_tiles : 1);
     if (want < 1) want = 1;
     if (want > col_tiles) want = col_tiles;
@@ -176,66 +182,66 @@ SplitPlan plan_splits(int rows, int rows_cta, int MS, int sm_count, int ctas_per
     return pl;
 }
 // resident CTAs per SM of the kernel that will run (cudaOccupancy..., cached per instantiation)
-int occ_fwd(int pc, int DP) {
+int occ_fwd(int pc, Shape sh) {
     int n;
     switch (pc) {
-        case 1: n = occ_fwd_p1(DP); break;
-        case 2: n = occ_fwd_p2(DP); break;
-        case 3: n = occ_fwd_p3(DP); break;
-        case 4: n = occ_fwd_p4(DP); break;
-        default: n = occ_fwd_p0(DP); break;
+        case 1: n = occ_fwd_p1(sh.DP, sh.F); break;
+        case 2: n = occ_fwd_p2(sh.DP, sh.F); break;
+        case 3: n = occ_fwd_p3(sh.DP, sh.F); break;
+        case 4: n = occ_fwd_p4(sh.DP, sh.F); break;
+        default: n = occ_fwd_p0(sh.DP, sh.F); break;
     }
     return n < 1 ? 1 : n;
 }
-int occ_bwd(int pc, int DP) {
+int occ_bwd(int pc, Shape sh) {
     int n;
     switch (pc) {
-        case 1: n = occ_bwd_p1(DP); break;
-        case 2: n = occ_bwd_p2(DP); break;
-        case 3: n = occ_bwd_p3(DP); break;
-        case 4: n = occ_bwd_p4(DP); break;
-        default: n = occ_bwd_p0(DP); break;
+        case 1: n = occ_bwd_p1(sh.DP, sh.F); break;
+        case 2: n = occ_bwd_p2(sh.DP, sh.F); break;
+        case 3: n = occ_bwd_p3(sh.DP, sh.F); break;
+        case 4: n = occ_bwd_p4(sh.DP, sh.F); break;
+        default: n = occ_bwd_p0(sh.DP, sh.F); break;
     }
     return n < 1 ? 1 : n;
 }
 // The split plan only depends on (rows, MS, DP, #SMs) -- NOT on the exponent -- so that the workspace queries
 // (which do not know p) and the launches agree: the most common occupancy of the family is used (p = 2).
-SplitPlan plan_fwd(int B, int M, int DP, int sms) {
-    const int R = fwd_rows_per_thread(DP);
-    return plan_splits(B, rows_per_cta(R), M, sms, occ_fwd(2, DP));
+SplitPlan plan_fwd(int B, int M, Shape sh, int sms) {
+    const int R = fwd_rows_per_thread(sh.DP);
+    return plan_splits(B, rows_per_cta(R, sh.F), M, tile_rows(sh.F), sms, occ_fwd(2, sh));
 }
-SplitPlan plan_bwd(int rows, int MS, int DP, int sms) {
-    const int R = bwd_rows_per_thread(DP);
-    return plan_splits(rows, rows_per_cta(R), MS, sms, occ_bwd(2, DP));
-}
-
-int dispatch_fwd(int pc, int DP, const FwdParams& q, dim3 g, cudaStream_t s) {
-    switch (pc) {
-        case 1: return launch_fwd_p1(DP, q, g, s);
-        case 2: return launch_fwd_p2(DP, q, g, s);
-        case 3: return launch_fwd_p3(DP, q, g, s);
-        case 4: return launch_fwd_p4(DP, q, g, s);
-        default: return launch_fwd_p0(DP, q, g, s);
-    }
-}
-int dispatch_bwd(int pc, int DP, const BwdParams& q, dim3 g, cudaStream_t s) {
-    switch (pc) {
-        case 1: return launch_bwd_p1(DP, q, g, s);
-        case 2: return launch_bwd_p2(DP, q, g, s);
-        case 3: return launch_bwd_p3(DP, q, g, s);
-        case 4: return launch_bwd_p4(DP, q, g, s);
-        default: return launch_bwd_p0(DP, q, g, s);
-    }
+SplitPlan plan_bwd(int rows, int MS, Shape sh, int sms) {
+    const int R = bwd_rows_per_thread(sh.DP);
+    return plan_splits(rows, rows_per_cta(R, sh.F), MS, tile_rows(sh.F), sms, occ_bwd(2, sh));
 }
 
-int check_common(int B, int M, int d, float p, float tau, int use_pow, int* DP, DeviceInfo* di) {
+int dispatch_fwd(int pc, Shape sh, const FwdParams& q, dim3 g, cudaStream_t s) {
+    switch (pc) {
+        case 1: return launch_fwd_p1(sh.DP, sh.F, q, g, s);
+        case 2: return launch_fwd_p2(sh.DP, sh.F, q, g, s);
+        case 3: return launch_fwd_p3(sh.DP, sh.F, q, g, s);
+        case 4: return launch_fwd_p4(sh.DP, sh.F, q, g, s);
+        default: return launch_fwd_p0(sh.DP, sh.F, q, g, s);
+    }
+}
+int dispatch_bwd(int pc, Shape sh, const BwdParams& q, dim3 g, cudaStream_t s) {
+    switch (pc) {
+        case 1: return launch_bwd_p1(sh.DP, sh.F, q, g, s);
+        case 2: return launch_bwd_p2(sh.DP, sh.F, q, g, s);
+        case 3: return launch_bwd_p3(sh.DP, sh.F, q, g, s);
+        case 4: return launch_bwd_p4(sh.DP, sh.F, q, g, s);
+        default: return launch_bwd_p0(sh.DP, sh.F, q, g, s);
+    }
+}
+
+int check_common(int B, int M, int d, float p, float tau, int use_pow, Shape* sh, DeviceInfo* di) {
     CLICA_REQUIRE(B >= 1 && M >= 1 && d >= 1, CLICA_E_BADARG, "lpnce: need B, M, d >= 1 (got %d, %d, %d)", B, M, d);
     CLICA_REQUIRE(tau > 0.f, CLICA_E_BADARG, "lpnce: tau must be > 0 (got %g)", (double)tau);
     CLICA_REQUIRE(p >= 1.f, CLICA_E_UNSUPPORTED,
                   "lpnce: p = %g < 1 (losses.py:433-442 branch) is not implemented by the CUDA path", (double)p);
     CLICA_REQUIRE(use_pow == 1, CLICA_E_UNSUPPORTED, "lpnce: pow=False is not implemented by the CUDA path");
-    *DP = pick_dp(d);
-    CLICA_REQUIRE(*DP > 0, CLICA_E_UNSUPPORTED, "lpnce: feature width d = %d > 40 is not implemented yet", d);
+    *sh = pick_shape(d);
+    CLICA_REQUIRE(sh->DP > 0, CLICA_E_UNSUPPORTED, "lpnce: feature width d = %d > 320 is not implemented", d);
     int rc = get_device_info(di);
     if (rc) return rc;
     return 0;
@@ -268,8 +274,8 @@ BwdWs carve_bwd(void* ws, int nL, int B, int rowsA, int nsA, int rowsB, int nsB,
     return w;
 }
 
-inline int is_flat16(const float* S, int ldS, int d, int DP) {
-    return (d == 2 * DP) && (ldS == d) && (((uintptr_t)S & 15u) == 0);
+inline int is_flat16(const float* S, int ldS, int d, Shape sh) {
+    return (sh.F == 1) && (d == 2 * sh.DP) && (ldS == d) && (((uintptr_t)S & 15u) == 0);
 }
 
 }  // namespace
@@ -279,9 +285,9 @@ using namespace clica;
 
 extern "C" size_t clica_lpnce_workspace_bytes(int B, int M, int d) {
     DeviceInfo di;
-    int DP = pick_dp(d);
-    if (B < 1 || M < 1 || DP < 0 || get_device_info(&di)) return 0;
-    SplitPlan pl = plan_fwd(B, M, DP, di.sm_count);
+    Shape sh = pick_shape(d);
+    if (B < 1 || M < 1 || sh.DP < 0 || get_device_info(&di)) return 0;
+    SplitPlan pl = plan_fwd(B, M, sh, di.sm_count);
     return carve_fwd(nullptr, B, pl.nsplit).bytes;
 }
 
@@ -289,24 +295,24 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
                                int B, int M, int d, float p, float tau, float alpha, int include_pos,
                                int use_pow, float* loss_i, float* lse, float* pos, float* rowstat,
                                float* scalars3, void* ws, size_t ws_bytes, void* stream) {
-    int DP; DeviceInfo di;
-    int rc = check_common(B, M, d, p, tau, use_pow, &DP, &di);
+    Shape sh; DeviceInfo di;
+    int rc = check_common(B, M, d, p, tau, use_pow, &sh, &di);
     if (rc) return rc;
     CLICA_REQUIRE(z1 && z2 && z3 && loss_i && lse && pos && rowstat && scalars3 && ws, CLICA_E_BADARG, "lpnce_fwd: null pointer");
     CLICA_REQUIRE(((uintptr_t)rowstat & 7u) == 0, CLICA_E_ALIGN, "lpnce_fwd: rowstat must be 8-byte aligned");
     CLICA_REQUIRE(ld1 >= d && ld2 >= d && ld3 >= d, CLICA_E_BADARG, "lpnce_fwd: leading dimension < d");
     CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_fwd: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    SplitPlan pl = plan_fwd(B, M, DP, di.sm_count);
+    SplitPlan pl = plan_fwd(B, M, sh, di.sm_count);
     FwdWs w = carve_fwd(ws, B, pl.nsplit);
     CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_fwd: workspace %zu < %zu bytes", ws_bytes, w.bytes);
 
     FwdParams q;
     q.O = z1; q.ldO = ld1; q.BO = B; q.S = z3; q.ldS = ld3; q.MS = M; q.d = d;
     q.coef = kLog2e / tau; q.pg = p;
-    q.tiles_per_split = pl.tiles_per_split; q.flat16 = is_flat16(z3, ld3, d, DP);
+    q.tiles_per_split = pl.tiles_per_split; q.flat16 = is_flat16(z3, ld3, d, sh);
     q.part_m = w.part_m; q.part_s = w.part_s; q.part_stride = B; q.counter = w.counter;
-    { LaunchScope ls(st, kFamLossFwd); rc = dispatch_fwd(p_code(p), DP, q, dim3(pl.row_tiles, pl.nsplit, 1), st); }
+    { LaunchScope ls(st, kFamLossFwd); rc = dispatch_fwd(p_code(p), sh, q, dim3(pl.row_tiles, pl.nsplit, 1), st); }
     if (rc) return rc;
 
     FinParams f;
@@ -322,10 +328,10 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
 
 extern "C" size_t clica_lpnce_bwd_workspace_bytes(int B, int M, int d) {
     DeviceInfo di;
-    int DP = pick_dp(d);
-    if (B < 1 || M < 1 || DP < 0 || get_device_info(&di)) return 0;
-    SplitPlan a = plan_bwd(B, M, DP, di.sm_count), b = plan_bwd(M, B, DP, di.sm_count);
-    return carve_bwd(nullptr, B, B, B, a.nsplit, M, b.nsplit, 2 * DP).bytes;
+    Shape sh = pick_shape(d);
+    if (B < 1 || M < 1 || sh.DP < 0 || get_device_info(&di)) return 0;
+    SplitPlan a = plan_bwd(B, M, sh, di.sm_count), b = plan_bwd(M, B, sh, di.sm_count);
+    return carve_bwd(nullptr, B, B, B, a.nsplit, M, b.nsplit, 2 * sh.DP * sh.F).bytes;
 }
 
 extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
@@ -333,8 +339,8 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
                                int use_pow, const float* rowstat, const float* pos, const float* g_mean,
                                const float* g_loss_i, float* g_z1, int ldg1, float* g_z2, int ldg2,
                                float* g_z3, int ldg3, void* ws, size_t ws_bytes, void* stream) {
-    int DP; DeviceInfo di;
-    int rc = check_common(B, M, d, p, tau, use_pow, &DP, &di);
+    Shape sh; DeviceInfo di;
+    int rc = check_common(B, M, d, p, tau, use_pow, &sh, &di);
     if (rc) return rc;
     CLICA_REQUIRE(z1 && z2 && z3 && rowstat && pos && ws, CLICA_E_BADARG, "lpnce_bwd: null pointer");
     CLICA_REQUIRE(((uintptr_t)rowstat & 7u) == 0, CLICA_E_ALIGN, "lpnce_bwd: rowstat must be 8-byte aligned");
@@ -343,8 +349,8 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
                   "lpnce_bwd: gradient leading dimension < d");
     CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_bwd: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int TW = 2 * DP;
-    SplitPlan pa = plan_bwd(B, M, DP, di.sm_count), pb = plan_bwd(M, B, DP, di.sm_count);
+    const int TW = 2 * sh.DP * sh.F;
+    SplitPlan pa = plan_bwd(B, M, sh, di.sm_count), pb = plan_bwd(M, B, sh, di.sm_count);
     BwdWs w = carve_bwd(ws, B, B, B, pa.nsplit, M, pb.nsplit, TW);
     CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_bwd: workspace %zu < %zu bytes", ws_bytes, w.bytes);
 
@@ -365,7 +371,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
             BwdRole& r = q.role[q.nroles++];
             r.O = z1; r.ldO = ld1; r.BO = B; r.S = z3; r.ldS = ld3; r.MS = M;
             r.LO = (const float2*)rowstat; r.LS = nullptr; r.ES = nullptr; r.EO = nullptr;
-            r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z3, ld3, d, DP);
+            r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z3, ld3, d, sh);
             r.part = w.partA; r.part_rows = B; r.row_tiles = pa.row_tiles;
             gx = max(gx, pa.row_tiles); gy = max(gy, pa.nsplit);
         }
@@ -373,11 +379,11 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
             BwdRole& r = q.role[q.nroles++];
             r.O = z3; r.ldO = ld3; r.BO = M; r.S = z1; r.ldS = ld1; r.MS = B;
             r.LO = nullptr; r.LS = (const float2*)rowstat; r.ES = w.E; r.EO = nullptr;
-            r.tiles_per_split = pb.tiles_per_split; r.nsplit = pb.nsplit; r.flat16 = is_flat16(z1, ld1, d, DP);
+            r.tiles_per_split = pb.tiles_per_split; r.nsplit = pb.nsplit; r.flat16 = is_flat16(z1, ld1, d, sh);
             r.part = w.partB; r.part_rows = M; r.row_tiles = pb.row_tiles;
             gx = max(gx, pb.row_tiles); gy = max(gy, pb.nsplit);
         }
-        { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(gx, gy, q.nroles), st); }
+        { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), sh, q, dim3(gx, gy, q.nroles), st); }
         if (rc) return rc;
     }
     if (g_z1 || g_z2) {
@@ -407,10 +413,10 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
 
 extern "C" size_t clica_lpnce_bwd_sharded_workspace_bytes(int B, int M, int d) {
     DeviceInfo di;
-    int DP = pick_dp(d);
-    if (B < 1 || M < 1 || DP < 0 || get_device_info(&di)) return 0;
-    SplitPlan a = plan_bwd(B, M, DP, di.sm_count);
-    return carve_bwd(nullptr, M, B, B, a.nsplit, B, a.nsplit, 2 * DP).bytes;
+    Shape sh = pick_shape(d);
+    if (B < 1 || M < 1 || sh.DP < 0 || get_device_info(&di)) return 0;
+    SplitPlan a = plan_bwd(B, M, sh, di.sm_count);
+    return carve_bwd(nullptr, M, B, B, a.nsplit, B, a.nsplit, 2 * sh.DP * sh.F).bytes;
 }
 
 extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const float* z2_local, int ld2,
@@ -419,8 +425,8 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
                                        float tau, float alpha, int include_pos, const float* g_scale,
                                        float* g_z1, int ldg1, float* g_z2, int ldg2,
                                        void* ws, size_t ws_bytes, void* stream) {
-    int DP; DeviceInfo di;
-    int rc = check_common(B, M, d, p, tau, 1, &DP, &di);
+    Shape sh; DeviceInfo di;
+    int rc = check_common(B, M, d, p, tau, 1, &sh, &di);
     if (rc) return rc;
     CLICA_REQUIRE(z1_local && z2_local && z_all && rowstat_all && pos_local && g_z1 && ws, CLICA_E_BADARG,
                   "lpnce_bwd_sharded: null pointer");
@@ -430,8 +436,8 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
                   "lpnce_bwd_sharded: leading dimension < d");
     CLICA_REQUIRE(((uintptr_t)ws & 15u) == 0, CLICA_E_ALIGN, "lpnce_bwd_sharded: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int TW = 2 * DP;
-    SplitPlan pa = plan_bwd(B, M, DP, di.sm_count);
+    const int TW = 2 * sh.DP * sh.F;
+    SplitPlan pa = plan_bwd(B, M, sh, di.sm_count);
     BwdWs w = carve_bwd(ws, M, B, B, pa.nsplit, B, pa.nsplit, TW);
     CLICA_REQUIRE(ws_bytes >= w.bytes, CLICA_E_WORKSPACE, "lpnce_bwd_sharded: workspace %zu < %zu bytes", ws_bytes, w.bytes);
 
@@ -456,11 +462,11 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     {
         BwdRole& r = q.role[0];
         r.O = z1_local; r.ldO = ld1; r.BO = B; r.S = z_all; r.ldS = ld3; r.MS = M;
-        r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z_all, ld3, d, DP);
+        r.tiles_per_split = pa.tiles_per_split; r.nsplit = pa.nsplit; r.flat16 = is_flat16(z_all, ld3, d, sh);
         r.part_rows = B; r.row_tiles = pa.row_tiles;
         r.LO = stat_all + row0; r.EO = w.E + row0; r.LS = stat_all; r.ES = w.E; r.part = w.partB;
     }
-    { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), DP, q, dim3(pa.row_tiles, pa.nsplit, 1), st); }
+    { LaunchScope ls(st, kFamLossBwd); rc = dispatch_bwd(p_code(p), sh, q, dim3(pa.row_tiles, pa.nsplit, 1), st); }
     if (rc) return rc;
 
     ReduceParams r;

@@ -10,7 +10,7 @@ of the reference on ``sys.path`` that import resolves here:
 * every other name of the reference module (SimCLRLoss, CLLoss, ...) is re-exported from the reference
   checkout when one is reachable -- none of them is on the hot path.
 * inputs outside the kernel's domain (CPU tensors = BASELINE config 1 "reference plumbing", p < 1,
-  pow=False, non-fp32, d > 40) are handed to the reference's own ``LpSimCLRLoss.loss`` -- explicitly, with
+  pow=False, non-fp32, d > 320) are handed to the reference's own ``LpSimCLRLoss.loss`` -- explicitly, with
   a one-time warning -- or raise if no reference checkout is reachable.  On a CUDA fp32 input inside the
   domain there is exactly one path and a missing CUDA library raises.
 """
@@ -38,7 +38,7 @@ else:
         def __call__(self, z1, z2_con_z1, z3, z1_rec, z2_con_z1_rec, z3_rec):
             return self.loss(z1, z2_con_z1, z3, z1_rec, z2_con_z1_rec, z3_rec)
 
-_MAX_D = 40
+_MAX_D = 320
 _warned = set()
 
 

@@ -77,7 +77,8 @@ def test_pow_false_is_refused_not_approximated(cuda_device):
 
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 2.5])
-@pytest.mark.parametrize("B,M,d", [(300, 517, 10), (129, 128, 3), (257, 1031, 40), (64, 2000, 16), (1000, 999, 33)])
+@pytest.mark.parametrize("B,M,d", [(300, 517, 10), (129, 128, 3), (257, 1031, 40), (64, 2000, 16), (1000, 999, 33),
+                                   (130, 257, 128), (64, 100, 64), (96, 201, 100), (40, 70, 256)])
 def test_random_shapes_against_c_oracle(p, B, M, d, cuda_device):
     from oracle import c_oracle
     rng = np.random.RandomState(B * 7 + M + d)
@@ -89,6 +90,26 @@ def test_random_shapes_against_c_oracle(p, B, M, d, cuda_device):
     out = _run(z1, z2, z3, float(p), tau, 0.5, True, cuda_device)
     ref = c_oracle.lpnce(z1, z2, z3, p, tau, 0.5, include_pos=True)
     _check(out, ref, roll=False, grad_tol=GRAD_TOL if p != 2.5 else 3e-5)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("B,d", [(384, 128), (200, 10), (100, 72)])
+def test_rolled_negatives_use_the_merged_backward(p, B, d, cuda_device):
+    """z3 = torch.roll(z1, 1, 0) (main_mlp.py:272): autograd-detected, single merged backward pass; also the
+    feature-split kernels (d > 40: 2 / 4 / 8 lanes per pair) of BASELINE's sweep config (d = 128)."""
+    from clica_b200 import functional as F
+    from oracle import c_oracle
+    rng = np.random.RandomState(B + d + p)
+    z1 = (rng.randn(B, d) * 0.4).astype(np.float32)
+    z2 = (z1 + 0.05 * rng.randn(B, d)).astype(np.float32)
+    a = torch.tensor(z1, device=cuda_device, requires_grad=True)
+    b = torch.tensor(z2, device=cuda_device, requires_grad=True)
+    n = torch.roll(a, 1, 0)
+    assert F.is_row_roll_of(n, a)
+    out = _run(z1, z2, None, float(p), 0.9, 0.5, True, cuda_device, roll=True)
+    ref = c_oracle.lpnce(z1, z2, np.roll(z1, 1, 0), p, 0.9, 0.5, include_pos=True)
+    ref["g1"] = ref["g1"] + np.roll(ref["g3"], -1, 0)
+    _check(out, ref, roll=True)
 
 
 def test_strided_views_and_none_arguments(cuda_device):
