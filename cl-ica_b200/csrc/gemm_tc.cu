@@ -32,6 +32,7 @@ namespace {
 constexpr int BM = 128, BK = 32;                       // BK fp32 = 128 bytes = one swizzle span; BN = 128 or 256 (template)
 constexpr int kTcThreads = 320;                          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
+constexpr size_t kEpiStageBytes = 8 * 4096;                 // one 32 x 32 fp32 staging block per epilogue warp
 
 struct TcKernelParams {
     int Mo, No;
@@ -44,6 +45,8 @@ struct TcKernelParams {
     float* out_hi; float* out_lo; int ldp;
     uint32_t mn_lbo, mn_sbo, mn_lt;   // MN-major descriptor fields (defaults: BK*128, 512, 1)
     float* colsum;                    // optional [No]: += column sums of the stored values (pre-zeroed by the caller)
+    int out_tma;                      // kTcAtomic: tmOh describes `out`, partial sums leave as TMA reduce-adds
+    long long* timing;                // debug (tools/gemm_phase_probe.py): [grid][8] clock64 stamps of the CTA's phases
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -78,6 +81,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+// smem -> global tile store through the TMA (bulk async-group completion); the tensor map clips rows / columns
+// that fall outside the tensor, so ragged tiles need no predication
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(x), "r"(y) : "memory");
+}
+// smem tile added (fp32) into the global tensor by the TMA: split-K partial sums, one request per 128-byte line
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int x, int y) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -157,6 +175,7 @@ template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                const TcKernelParams q) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -173,17 +192,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const uint32_t stage_bytes = (uint32_t)nplanes * (kABytes + kBBytes);
     const int num_m = (q.Mo + BM - 1) / BM, num_n = (q.No + BN - 1) / BN;
     const int total = num_m * num_n * q.splits;
+    long long* const tm = q.timing ? q.timing + (size_t)blockIdx.x * 8 : nullptr;
+    if (tm && threadIdx.x == 0) tm[0] = clock64();
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < q.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+    constexpr uint32_t kTmemCols = (BN <= 128) ? 256u : 512u;       // two accumulators; allocations are powers of two
+    if (warp == 1) tmem_alloc(&tmem_slot, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    if (tm && threadIdx.x == 0) tm[1] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -207,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     if (nplanes == 2) load_operand<BM>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s]);
                     load_operand<BN>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s]);
                     if (nplanes == 2) load_operand<BN>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s]);
+                    if (tm && it == 0) tm[2] = clock64();
                 }
             }
         }
@@ -232,6 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
                     mbar_wait(&full_bar[s], ph);
                     tcgen05_fence_after();
+                    if (tm && it == 0) tm[3] = clock64();
                     const uint32_t sa = tiles + s * stage_bytes;
                     const uint32_t a_hi = sa, a_lo = sa + kABytes;
                     const uint32_t b_hi = sa + nplanes * kABytes, b_lo = b_hi + kBBytes;
@@ -253,21 +278,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     umma_commit(&empty_bar[s]);            // stage reusable once these MMAs have read it
                 }
                 umma_commit(&tmem_full_bar[as]);           // accumulator complete
+                if (tm) tm[4] = clock64();
             }
         }
     } else {
         // ===== epilogue: warps 2..9 (8 warps).  TMEM lane quarter = warp % 4; the two warps of a quarter take the
-        // even / odd 32-column chunks.  The epilogue is latency-bound (TMEM load -> global mask load -> stores), so:
-        //   * twice the warps = twice the memory-level parallelism,
-        //   * the bias slice of the tile is staged in shared memory once per tile (broadcast LDS instead of LDG),
-        //   * the activation-mask values of the NEXT chunk are prefetched while the current one is processed,
-        //   * every thread owns 32 consecutive columns of its row = one full 128-byte line, written with 8 STG.128
-        //     (split-K accumulation: 8 x red.global.add.v4.f32).
+        // even / odd 32-column chunks.  A thread reads one accumulator row (32 consecutive columns per tcgen05.ld).
+        // Planar outputs leave through the TMA: the warp stages its 32 x 32 block in a private 4 KB shared-memory
+        // buffer (128B-swizzled: conflict-free STS.128) and one lane issues a bulk tensor store -- whole 128-byte
+        // lines per request instead of 32 partial-sector writes per STG instruction, and rows / columns past the
+        // tensor edge are clipped by the tensor map.  The staged block also yields the column sums (bias
+        // gradients) with 32 conflict-free LDS per lane instead of 160 shuffles.
         const int ew = warp - 2;
         const int wq = warp & 3;
         const int half = ew >> 2;
         const int etid = threadIdx.x - 64;                     // 0..255 among the epilogue threads
         const bool aux_vec = (q.aux != nullptr) && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15u) == 0);
+        uint8_t* const sbuf = smem_raw + (tiles - smem_u32(smem_raw)) + (uint32_t)q.stages * stage_bytes + (uint32_t)ew * 4096u;
+        const uint32_t sbuf_u32 = smem_u32(sbuf);
+        float4* const srow = reinterpret_cast<float4*>(sbuf + lane * 128);
+        // stage the warp's 32 x 32 block (thread = row, u = its 32 columns) once the previous store has read the buffer
+        auto stage = [&](const float (&u)[32]) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) srow[j ^ (lane & 7)] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+        };
+        // column `lane` of the staged block summed over its 32 rows
+        auto staged_colsum = [&]() {
+            float t = 0.f;
+            const uint32_t cw = (uint32_t)(lane >> 2), ci = (uint32_t)(lane & 3) * 4u;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) t += *reinterpret_cast<const float*>(sbuf + r * 128 + ((cw ^ (uint32_t)(r & 7)) << 4) + ci);
+            return t;
+        };
         uint32_t tile_iter = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
             const int m0 = (w % num_m) * BM;
@@ -302,6 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (use_aux) load_aux(half);
             mbar_wait(&tmem_full_bar[as], (tile_iter >> 1) & 1u);
             tcgen05_fence_after();
+            if (tm && etid == 0 && tile_iter == 0) tm[5] = clock64();
 #pragma unroll 1
             for (int chunk = half; chunk < BN / 32; chunk += 2) {
                 float v[32];
@@ -326,19 +373,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     if (chunk + 2 < BN / 32) load_aux(chunk + 2);       // prefetch for the next iteration
                 }
                 if (nvalid <= 0) continue;                              // warp-uniform
-                if (q.colsum != nullptr && q.epi != kTcAtomic) {
-                    // bias gradient of the layer whose pre-activation gradient this is: butterfly-reduce each column
-                    // over the warp's 32 rows (rows past M contribute 0), lane j keeps column j
-                    float mine = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float tot = warp_sum(row_ok ? v[j] : 0.f);
-                        if (lane == j) mine = tot;
-                    }
-                    if (lane < nvalid) atomicAdd(q.colsum + col0 + lane, mine);
+                if (q.epi == kTcAtomic && q.out_tma) {
+                    stage(v);
+                    if (lane == 0) { tma_reduce_add_2d(&tmOh, sbuf_u32, col0, m0 + wq * 32); bulk_commit(); }
+                    continue;
                 }
-                if (!row_ok) continue;
                 if (q.epi == kTcAtomic) {
+                    if (!row_ok) continue;
                     float* op = q.out + (size_t)row * q.ldo + col0;
                     if (nvalid == 32 && (q.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(q.out) & 15u) == 0)) {
 #pragma unroll
@@ -350,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     }
                     continue;
                 }
-                if (q.out != nullptr) {
+                if (q.out != nullptr && row_ok) {
                     float* op = q.out + (size_t)row * q.ldo + col0;
                     if (nvalid == 32 && (q.ldo & 3) == 0) {
 #pragma unroll
@@ -361,49 +402,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             if (j < nvalid) op[j] = v[j];
                     }
                 }
-                if (q.out_hi != nullptr) {
-                    float* hp = q.out_hi + (size_t)row * q.ldp + col0;
-                    float* lp = (q.out_lo != nullptr) ? q.out_lo + (size_t)row * q.ldp + col0 : nullptr;
-                    if (lp != nullptr) {
-                        if (nvalid == 32) {
+                const bool want_sum = (q.colsum != nullptr);
+                if (q.out_hi == nullptr && !want_sum) continue;
+                // rows past M hold zero accumulators (TMA zero-fill) but a bias may have been added: keep them out of
+                // the column sums (the tensor map keeps them out of the stores)
+                if (want_sum && !row_ok) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 h, l;
-                                h.x = round_to_tf32(v[j]); l.x = round_to_tf32(v[j] - h.x);
-                                h.y = round_to_tf32(v[j + 1]); l.y = round_to_tf32(v[j + 1] - h.y);
-                                h.z = round_to_tf32(v[j + 2]); l.z = round_to_tf32(v[j + 2] - h.z);
-                                h.w = round_to_tf32(v[j + 3]); l.w = round_to_tf32(v[j + 3] - h.w);
-                                *reinterpret_cast<float4*>(hp + j) = h;
-                                *reinterpret_cast<float4*>(lp + j) = l;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) { const float h = round_to_tf32(v[j]); hp[j] = h; lp[j] = round_to_tf32(v[j] - h); }
-                        }
-                    } else {
-                        if (nvalid == 32) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(hp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) hp[j] = v[j];
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
+                float csum = 0.f;
+                const int wrow0 = m0 + wq * 32;
+                if (q.out_hi != nullptr && q.out_lo != nullptr) {
+                    float h[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { h[j] = round_to_tf32(v[j]); v[j] = round_to_tf32(v[j] - h[j]); }
+                    stage(h);
+                    if (lane == 0) { tma_store_2d(&tmOh, sbuf_u32, col0, wrow0); bulk_commit(); }
+                    if (want_sum) csum = staged_colsum();
+                    stage(v);
+                    if (lane == 0) { tma_store_2d(&tmOl, sbuf_u32, col0, wrow0); bulk_commit(); }
+                    if (want_sum) csum += staged_colsum();
+                } else {
+                    stage(v);
+                    if (q.out_hi != nullptr && lane == 0) { tma_store_2d(&tmOh, sbuf_u32, col0, wrow0); bulk_commit(); }
+                    if (want_sum) csum = staged_colsum();
+                }
+                if (want_sum && lane < nvalid) atomicAdd(q.colsum + col0 + lane, csum);
             }
             // this warp has read its share of the accumulator: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (tm && etid == 0) tm[6] = clock64();
         }
+        if (lane == 0) bulk_wait_all0();      // the staging buffer must outlive the last bulk store
+        __syncwarp();
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (tm && threadIdx.x == 0) tm[7] = clock64();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -498,6 +538,39 @@ int get_tensor_map(const float* ptr, int rows, int cols, int ld, int box_rows, b
 
 }  // namespace
 
+// Tile width and split-K factor.  Measured (tools/gemm_phase_probe.py): once the ring is flowing, a CTA's main loop
+// is paced by the operand bytes it pulls through the TMA (~95-105 GB/s per SM whether 96 or 148 CTAs run), not by
+// the tensor pipe, so an item costs  kb * (BM + BN) * BK * 4 * planes  bytes of loads plus an epilogue that moves
+// BM * BN * 4 * planes output bytes (weighted x4: write / reduce traffic drains slower than loads stream), and
+// a persistent CTA works through ceil(items / #SMs) items.  Pick the (BN, splits) with the shortest makespan;
+// ties go to the wider tile (less operand traffic per flop).
+struct TilePlan { int bn; int splits; };
+TilePlan plan_tiles(int Mo, int No, int kb_total, int sm_count, bool split_k) {
+    const int forced = env_int("CLICA_TC_BN", 0);
+    const int widths[3] = {256, 192, 128};
+    TilePlan best = {256, 1};
+    double best_cost = 1e300;
+    for (int i = 0; i < 3; ++i) {
+        const int bn = widths[i];
+        if (forced == 128 || forced == 192 || forced == 256) { if (bn != forced) continue; }
+        else if (bn > 128 && No <= bn - 64) continue;           // a narrower tile already covers the whole output
+        const long long tiles = (long long)ceil_div(Mo, BM) * ceil_div(No, bn);
+        const int max_splits = split_k ? (kb_total / 4 > 0 ? kb_total / 4 : 1) : 1;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const int kb_per = ceil_div(kb_total, sp);
+            const int sp_eff = ceil_div(kb_total, kb_per);
+            if (sp_eff != sp) continue;                         // same work division as a smaller split count
+            const long long items = tiles * sp;
+            const long long waves = (items + sm_count - 1) / sm_count;
+            const double item_cost = (double)kb_per * (BM + bn) + 4.0 * bn * (split_k ? 2.0 : 1.0);
+            const double cost = (double)waves * item_cost;
+            if (cost < best_cost * 0.999) { best_cost = cost; best.bn = bn; best.splits = sp; }
+            if (items > 8LL * sm_count) break;
+        }
+    }
+    return best;
+}
+
 bool tc_shape_ok(int M_out, int N_out, int K_red) { return M_out >= 32 && N_out >= 32 && K_red >= 32; }
 
 int tc_split_planes(const float* src, int ld_src, int rows, int cols, float* hi, float* lo, int ld_dst, cudaStream_t st) {
@@ -514,10 +587,9 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
     const int nterms = g.A.lo ? 3 : 1;
     const int nplanes = (nterms == 3) ? 2 : 1;
-    // N = 256 per tcgen05.mma runs the tensor pipe at its peak rate (128 cycles; N = 128 takes 80.6, i.e. 79%:
-    // tools/mma_probe.cu) and needs 25% less operand traffic per flop; narrow outputs keep the 128-wide tile.
-    const int bn = (env_int("CLICA_TC_BN", g.No > 128 ? 256 : 128) == 256) ? 256 : 128;
-    CUtensorMap tAh, tAl, tBh, tBl;
+    const TilePlan tp = plan_tiles(g.Mo, g.No, ceil_div(g.Kr, BK), sm_count, g.epi == kTcAtomic && g.allow_split_k);
+    const int bn = tp.bn;
+    CUtensorMap tAh, tAl, tBh, tBl, tOh, tOl;
     int rc;
     // storage shape of each operand: K-major [MN rows][Kr cols] (box = tile rows); MN-major [Kr rows][MN cols] (box 32 rows)
     const int a_rows = g.a_mn_major ? g.Kr : g.Mo, a_cols = g.a_mn_major ? g.Mo : g.Kr, a_box = g.a_mn_major ? BK : BM;
@@ -530,44 +602,56 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     } else {
         tAl = tAh; tBl = tBh;
     }
+    // planar outputs are written by TMA stores of 32 x 32 blocks (clipped to [Mo x No] by the map)
+    tOh = tAh; tOl = tAh;
+    if (g.outp.hi && (rc = get_tensor_map(g.outp.hi, g.Mo, g.No, g.outp.ld, 32, false, &tOh))) return rc;
+    if (g.outp.lo && (rc = get_tensor_map(g.outp.lo, g.Mo, g.No, g.outp.ld, 32, false, &tOl))) return rc;
     TcKernelParams q;
+    q.out_tma = 0;
+    if (g.epi == kTcAtomic && (g.ldo % 4) == 0 && (((uintptr_t)g.out) & 15u) == 0 && env_int("CLICA_TC_RED_TMA", 1)) {
+        if ((rc = get_tensor_map(g.out, g.Mo, g.No, g.ldo, 32, false, &tOh))) return rc;
+        q.out_tma = 1;
+    }
     q.Mo = g.Mo; q.No = g.No;
     q.kb_total = ceil_div(g.Kr, BK);
     q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms;
     const size_t stage_bytes = (size_t)nplanes * (BM + bn) * BK * 4;
-    const size_t smem_budget = 196 * 1024;                      // + 18 KB of epilogue staging + alignment slack < 227 KB
-    q.stages = (int)(smem_budget / stage_bytes);
+    const size_t smem_cap = 227 * 1024 - 2048;                  // static shared memory (barriers, bias slice) + slack
+    const size_t smem_fixed = 1024 + kEpiStageBytes;            // alignment slack + 8 x 4 KB epilogue staging
+    q.stages = (int)((smem_cap - smem_fixed) / stage_bytes);
     if (q.stages > kMaxStages) q.stages = kMaxStages;
+    { const int so = env_int("CLICA_TC_STAGES", 0); if (so >= 1 && so < q.stages) q.stages = so; }   // debug override
     q.epi = g.epi; q.bias = g.bias; q.slope = g.slope; q.aux = g.aux; q.ldaux = g.ldaux;
     q.out = g.out; q.ldo = g.ldo; q.out_hi = g.outp.hi; q.out_lo = g.outp.lo; q.ldp = g.outp.ld;
     q.mn_lbo = (uint32_t)env_int("CLICA_TC_MN_LBO", BK * 128);   // debug overrides of the MN-major descriptor
     q.mn_sbo = (uint32_t)env_int("CLICA_TC_MN_SBO", 512);
     q.mn_lt = (uint32_t)env_int("CLICA_TC_MN_LT", 1);
     q.colsum = g.colsum;
-    const int tiles = ceil_div(g.Mo, BM) * ceil_div(g.No, bn);
-    int splits = 1;
-    if (g.epi == kTcAtomic && g.allow_split_k) {
-        splits = (sm_count + tiles - 1) / tiles;
-        const int max_splits = q.kb_total / 4 > 0 ? q.kb_total / 4 : 1;
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
+    {   // debug: CLICA_TC_TIMING_PTR = device address (decimal) of a [grid][8] int64 buffer
+        const char* tp = getenv("CLICA_TC_TIMING_PTR");
+        q.timing = tp ? (long long*)(uintptr_t)strtoull(tp, nullptr, 0) : nullptr;
     }
+    const int tiles = ceil_div(g.Mo, BM) * ceil_div(g.No, bn);
+    int splits = tp.splits;
     q.kb_per_split = ceil_div(q.kb_total, splits);
     splits = ceil_div(q.kb_total, q.kb_per_split);
     q.splits = splits;
-    const size_t smem = (size_t)q.stages * stage_bytes + 1024;
+    const size_t smem = (size_t)q.stages * stage_bytes + smem_fixed;
     static bool attr_set = false;
     if (!attr_set) {
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        const int max_dyn = (int)smem_cap;
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
         attr_set = true;
     }
     const int total = tiles * splits;
     const int grid = total < sm_count ? total : sm_count;
     {
         LaunchScope ls(st, kFamGemmTc);
-        if (bn == 256) gemm_tc_kernel<256><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, q);
-        else gemm_tc_kernel<128><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, q);
+        if (bn == 256) gemm_tc_kernel<256><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
+        else if (bn == 192) gemm_tc_kernel<192><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
+        else gemm_tc_kernel<128><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
     }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;

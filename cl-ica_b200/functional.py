@@ -7,6 +7,7 @@
 All tensors must be CUDA fp32; anything else raises.  Nothing here synchronises the host.
 """
 import ctypes
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -169,38 +170,48 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
     return arr
 
 
-# packed (GEMM-operand-format) copies of the encoder weights, keyed by the first weight's storage; refreshed whenever
-# any weight's version counter moves (i.e. once per optimizer step, while the encoder runs four times per step)
+# packed (GEMM-operand-format) copies of the encoder weights, keyed by the identity of the weight tensors (weak
+# references: a new tensor that happens to reuse a freed tensor's address and version must NOT hit) and refreshed
+# whenever any weight's version counter or storage moves (i.e. once per optimizer step, while the encoder runs
+# four times per step)
 _packed_cache = {}
 
 
-def _packed_weights(lib, Ws, widths, mode, dev) -> int:
-    """Device pointer (1024-byte aligned) of the packed weight planes, re-packed only when a weight changed."""
-    key = (dev.index, Ws[0].data_ptr(), int(mode))
+def _packed_weights(lib, Ws, widths, mode, dev):
+    """(device pointer (1024-byte aligned), owning buffer) of the packed weight planes; re-packed only on change."""
+    key = (dev.index, int(mode), tuple(id(W) for W in Ws))
     sig = tuple((W.data_ptr(), W._version) for W in Ws)
     stream = _stream_ptr(dev)
     hit = _packed_cache.get(key)
-    if hit is not None and hit[0] == sig and hit[2] == stream:
-        return hit[3]
+    alive = hit is not None and all(r() is W for r, W in zip(hit[4], Ws))
+    if alive and hit[0] == sig and hit[2] == stream:
+        return hit[3], hit[1]
     L = len(Ws)
     cw = (ctypes.c_int * (L + 1))(*widths)
     nbytes = lib.clica_mlp_packed_weight_bytes(L, cw, int(mode))
-    if hit is not None and hit[1].numel() >= nbytes + 1024 and hit[2] == stream:
+    if alive and hit[1].numel() >= nbytes + 1024 and hit[2] == stream:
         buf = hit[1]
     else:
         buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)     # the allocator only guarantees 512 B
     ptr = (buf.data_ptr() + 1023) // 1024 * 1024
     rc = lib.clica_mlp_pack_weights(L, cw, _ptr_array(Ws), int(mode), ptr, nbytes, stream)
     _lib.check(rc, "clica_mlp_pack_weights")
-    _packed_cache[key] = (sig, buf, stream, ptr)
-    return ptr
+    if len(_packed_cache) >= 16:                                            # drop entries whose tensors died
+        for k in [k for k, v in _packed_cache.items() if any(r() is None for r in v[4])]:
+            del _packed_cache[k]
+        if len(_packed_cache) >= 16:
+            _packed_cache.clear()
+    _packed_cache[key] = (sig, buf, stream, ptr, [weakref.ref(W) for W in Ws])
+    return ptr, buf
 
 
 class _MLP(torch.autograd.Function):
     """y = Linear_{L-1}( LeakyReLU( ... LeakyReLU(Linear_0(x)) ) ) through clica_mlp_fwd / clica_mlp_bwd."""
 
     @staticmethod
-    def forward(ctx, x, slope, mode, *params):
+    def forward(ctx, x, slope, mode, packed, *params):
+        # `packed` = (pointer, owning buffer) of the packed weight planes, resolved by mlp_forward() on the caller's
+        # own tensor objects; the backward reuses it (autograd guarantees the weights did not change in between)
         lib = _lib.load()
         x = _as_rows(x, "encoder input").contiguous()
         L = len(params) // 2
@@ -225,12 +236,12 @@ class _MLP(torch.autograd.Function):
             cw = (ctypes.c_int * (L + 1))(*widths)
             nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
             ws = _workspace(nbytes, dev, "mlp")
-            packed = _packed_weights(lib, Ws, widths, mode, dev)
             rc = lib.clica_mlp_fwd(L, cw, _ptr_array(Ws), _ptr_array(bs), _ptr_array(acts), M, float(slope),
-                                   int(mode), packed, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                                   int(mode), packed[0], ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_mlp_fwd")
         ctx.save_for_backward(*acts[:-1], *Ws)
         ctx.cfg = (L, widths, float(slope), int(mode), [b is not None for b in bs])
+        ctx.packed = packed
         return acts[-1]
 
     @staticmethod
@@ -256,16 +267,15 @@ class _MLP(torch.autograd.Function):
             cw = (ctypes.c_int * (L + 1))(*widths)
             nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
             ws = _workspace(nbytes, dev, "mlp")
-            packed = _packed_weights(lib, Ws, widths, mode, dev)
             rc = lib.clica_mlp_bwd(L, cw, _ptr_array(Ws), _ptr_array(acts), gy.data_ptr(), _ptr_array(dWs),
-                                   _ptr_array(dbs), _ptr(g_in), M, slope, mode, packed, 1,
+                                   _ptr_array(dbs), _ptr(g_in), M, slope, mode, ctx.packed[0], 1,
                                    ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             _lib.check(rc, "clica_mlp_bwd")
         grads = []
         for l in range(L):
-            grads.append(dWs[l] if ctx.needs_input_grad[3 + 2 * l] else None)
-            grads.append(dbs[l] if ctx.needs_input_grad[4 + 2 * l] else None)
-        return (g_in, None, None, *grads)
+            grads.append(dWs[l] if ctx.needs_input_grad[4 + 2 * l] else None)
+            grads.append(dbs[l] if ctx.needs_input_grad[5 + 2 * l] else None)
+        return (g_in, None, None, None, *grads)
 
 
 def mlp_forward(x, weights: List[torch.Tensor], biases: List[torch.Tensor], slope: float = 0.01,
@@ -276,7 +286,13 @@ def mlp_forward(x, weights: List[torch.Tensor], biases: List[torch.Tensor], slop
     flat = []
     for W, b in zip(weights, biases):
         flat += [W, b]
-    return _MLP.apply(x, slope, mode, *flat)
+    if not weights or not weights[0].is_cuda:
+        raise RuntimeError("mlp_forward: expected CUDA weights (the CUDA path has no CPU fallback)")
+    dev = weights[0].device
+    widths = [weights[0].shape[1]] + [W.shape[0] for W in weights]
+    with torch.cuda.device(dev):
+        packed = _packed_weights(_lib.load(), list(weights), widths, int(mode), dev)
+    return _MLP.apply(x, slope, mode, packed, *flat)
 
 
 # ---- fused Adam -----------------------------------------------------------------------------------------

@@ -134,14 +134,21 @@ def allreduce_grads(params: List[torch.nn.Parameter], group=None) -> None:
         off += n
 
 
-def sharded_train_step(f, g, optimizer, z1_local, z2_local, p, tau=1.0, alpha=0.5, group=None, ops=CudaOps):
+def sharded_train_step(f, g, optimizer, z1_local, z2_local, p, tau=1.0, alpha=0.5, group=None, ops=CudaOps,
+                       z12_local=None):
     """The body of ``main_mlp.py:258-285`` (unsupervised branch) on one rank's shard of the global batch.
 
     Returns (global mean loss tensor, tensor([pos_mean, neg_mean])) -- 0-dim / 2-element device tensors; the
     caller decides when to ``.item()`` them."""
     optimizer.zero_grad()
-    a = f(g(z1_local))
-    b = f(g(z2_local))
+    if z12_local is not None:
+        # anchors and positives pre-concatenated by the caller ([2B, n]): one encoder pass over 2B rows
+        ab = f(g(z12_local))
+        B = z12_local.shape[0] // 2
+        a, b = ab[:B], ab[B:]
+    else:
+        a = f(g(z1_local))
+        b = f(g(z2_local))
     loss, _, parts = sharded_lp_infonce(a, b, p, tau, alpha, True, group, ops)
     loss.backward()
     allreduce_grads([prm for prm in f.parameters()], group)

@@ -140,3 +140,36 @@ def test_fused_adam_matches_torch_adam(cuda_device):
         o_ref.step(), o_fus.step()
     for a, b in zip(p_ref, p_fus):
         assert (a - b).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
+
+
+def test_packed_weight_cache_is_keyed_by_tensor_identity(cuda_device):
+    """A NEW weight tensor that reuses a freed tensor's address (and version 0) must not hit the packed-weight
+    cache of the old one (regression: stale planes made the 3rd same-shaped encoder of a process compute with
+    the 1st one's weights)."""
+    from clica_b200 import functional as F
+    widths = [10, 100, 500, 500, 100, 10]
+    x = torch.randn(640, widths[0], device=cuda_device)
+
+    def run(seed):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        Ws = [(torch.rand(widths[i + 1], widths[i], generator=g) * 2 - 1).div_(widths[i] ** 0.5).to(cuda_device) for i in range(5)]
+        bs = [torch.zeros(widths[i + 1], device=cuda_device) for i in range(5)]
+        ptr0 = Ws[0].data_ptr()
+        y = F.mlp_forward(x, Ws, bs, slope=0.01, mode=_lib_mode("3xtf32"))
+        ref = x
+        for l, (W, b) in enumerate(zip(Ws, bs)):
+            ref = ref.double() @ W.double().t() + b.double()
+            if l < 4:
+                ref = torch.nn.functional.leaky_relu(ref, 0.01)
+        return ptr0, (y.double() - ref).abs().max().item() / ref.abs().max().item()
+
+    ptrs = set()
+    for seed in range(4):
+        ptr0, err = run(seed)
+        ptrs.add(ptr0)
+        assert err <= 5e-5, (seed, err)
+    # (the caching allocator normally hands the same block back, which is exactly the hazardous case)
+
+
+def _lib_mode(name):
+    return MODES[name][0]
