@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--gemm-mode", default=os.environ.get("CLICA_GEMM_MODE", "3xtf32"))
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="anchors per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="time the eager step instead of the CUDA-graph replay (single GPU)")
+    ap.set_defaults(graph=os.environ.get("CLICA_GRAPH", "1") != "0")
     return ap.parse_args()
 
 
@@ -239,7 +242,7 @@ def run_ours(args):
     # twice the rows per launch); the e2e flavour below keeps the script's two separate calls
     z12_d = torch.cat([z1_d, z2_d], 0).contiguous()
 
-    def step_device():
+    def step_eager():
         if world == 1:
             opt.zero_grad(set_to_none=True)
             ab = h(z12_d)
@@ -250,6 +253,21 @@ def run_ours(args):
             return total
         total, parts = sharded.sharded_train_step(f, g, opt, z1_d, z2_d, p, tau, 0.5, z12_local=z12_d)
         return total
+
+    # single GPU: the same step recorded once into a CUDA graph (clica_b200.graphed.GraphedTrainStep) and
+    # replayed -- no host work between the ~45 kernels of a step.  CLICA_GRAPH=0 times the eager step instead.
+    step_mode = "eager"
+    graphed = None
+    if world == 1 and args.graph:
+        from clica_b200.graphed import GraphedTrainStep
+        graphed = GraphedTrainStep(f, g, crit, B_local, n, lr=1e-4, host_io=False)
+        graphed.stage(z1_d, z2_d)
+        step_mode = "cuda_graph"
+
+    def step_device():
+        if graphed is not None:
+            return graphed.replay()[0]
+        return step_eager()
 
     def barrier():
         if world > 1:
@@ -280,6 +298,8 @@ def run_ours(args):
     launches0 = lib.clica_launch_count(-1)
     ms_total, last = timed(step_device, args.steps)
     launches = lib.clica_launch_count(-1) - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps     # recorded once, executed once per replay
     ms_step = ms_total / args.steps
     value = B_global / (ms_step * 1e-3)
     loss_value = float(last.item())
@@ -289,7 +309,7 @@ def run_ours(args):
     prof_steps = min(args.steps, 20)
     _lib.check(lib.clica_prof_enable(1), "clica_prof_enable")
     for _ in range(prof_steps):
-        step_device()
+        step_eager()                                            # (events cannot bracket kernels inside a graph)
     ms_f = (ctypes.c_float * 7)()
     n_f = (ctypes.c_int * 7)()
     _lib.check(lib.clica_prof_collect(ms_f, n_f), "clica_prof_collect")
@@ -303,7 +323,8 @@ def run_ours(args):
     opt2 = torch.optim.Adam(f2.parameters(), lr=1e-4)
     h2 = lambda z: f2(g(z))
 
-    def step_e2e():
+    def step_e2e_eager():
+        # exactly what the unchanged main_mlp.py does per step on the drop-in modules
         z1 = z1_h.to(dev, non_blocking=True)
         z2 = z2_h.to(dev, non_blocking=True)
         if world == 1:
@@ -316,18 +337,33 @@ def run_ours(args):
             total, parts = sharded.sharded_train_step(f2, g, opt2, z1, z2, p, tau, 0.5)
         return total.item(), [float(x) for x in (parts.tolist() if torch.is_tensor(parts) else [q.item() for q in parts])]
 
-    for _ in range(max(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
+    def time_e2e(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    e2e_eager_ms = time_e2e(step_e2e_eager)
+    e2e_ms, e2e_mode = e2e_eager_ms, "eager drop-in modules (as main_mlp.py runs them)"
+    if world == 1 and args.graph:
+        # public API for a host-fed loop: GraphedTrainStep(host_io=True).step_host(z1_host, z2_host) stages the
+        # host latents in pinned memory; the graph copies them to the device, runs the step and copies
+        # (loss, pos_mean, neg_mean) back; step_host waits for that copy and returns Python floats
+        from clica_b200.graphed import GraphedTrainStep
+        torch.manual_seed(0)
+        f3 = encoders.get_mlp(n, n, [10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n]).to(dev)
+        graphed_io = GraphedTrainStep(f3, g, crit, B_local, n, lr=1e-4, host_io=True)
+        e2e_ms = time_e2e(lambda: graphed_io.step_host(z1_h, z2_h))
+        e2e_mode = "GraphedTrainStep.step_host (CUDA graph incl. H2D of the batch and D2H of the loss scalars)"
     e2e_value = B_global / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -377,7 +413,10 @@ def run_ours(args):
                        "tau": tau, "gemm_mode": args.gemm_mode, "parallelism": f"row-sharded x{world}, all-gathered negatives" if world > 1 else "single GPU",
                        "l2_policy": "no L2 flush: the step rewrites >126 MB of activations/gradients per iteration (inputs larger than L2 at c2: 2 x 109 MB saved activations)"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 2 * B_local * n * 4, "d2h_bytes_per_step": 12},
+                    "h2d_bytes_per_step": 2 * B_local * n * 4, "d2h_bytes_per_step": 12, "api": e2e_mode,
+                    "eager_dropin_ms_per_step": e2e_eager_ms,
+                    "eager_dropin_value": B_global / (e2e_eager_ms * 1e-3)},
+            "step_mode": step_mode,
             "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "loss": loss_value,
         }

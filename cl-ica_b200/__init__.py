@@ -6,6 +6,7 @@ Layout (only what the path needs):
   functional.py  autograd.Function wrappers: lp_infonce, mlp_forward, adam_step
   dropin/        modules named like the reference's (losses.py, encoders.py) so main_mlp.py runs unchanged
   optim.py       FusedAdam (torch.optim.Optimizer API) on clica_adam_step
+  graphed.py     GraphedTrainStep: the whole step as one CUDA graph (host batch in, loss scalars out)
   sharded.py     one-process-per-GPU step: batch shards + NCCL all-gather of encoder outputs
   launch.py      runs the reference's byte-identical main_mlp.py against the drop-in modules
 """
@@ -20,7 +21,7 @@ from ._lib import ClicaError, build  # noqa: E402,F401
 
 def __getattr__(name):
     # functional / optim / sharded import torch; keep `import clica_b200` itself light
-    if name in ("functional", "optim", "sharded", "launch"):
+    if name in ("functional", "optim", "sharded", "launch", "graphed"):
         import importlib
         return importlib.import_module("clica_b200." + name)
     raise AttributeError(name)

@@ -55,6 +55,8 @@ SIGNATURES = {
     "clica_prof_collect": (_c_int, [_vp, _vp]),
     "clica_adam_step": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _c_float, _c_float, _c_float,
                                  _i64, _c_float, _vp]),
+    "clica_adam_step_capturable": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _c_float, _c_float,
+                                            _c_float, _vp, _c_float, _vp]),
 }
 
 _lock = threading.Lock()

@@ -313,3 +313,30 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, step,
                                  _ptr_array(exp_avg_sqs), numel, float(lr), float(beta1), float(beta2),
                                  float(eps), int(step), float(grad_scale), _stream_ptr(dev))
         _lib.check(rc, "clica_adam_step")
+
+
+def adam_step_capturable(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, step_state, grad_scale=1.0):
+    """Fused Adam whose step count lives on the device (``step_state``: int64[2] CUDA tensor, zero before the
+    first step).  Safe to record into a CUDA graph: every replay advances the count and applies one update."""
+    lib = _lib.load()
+    if not params:
+        return
+    dev = params[0].device
+    for group in (params, grads, exp_avg_sqs, exp_avgs):
+        for t in group:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == dev):
+                raise RuntimeError("adam_step_capturable: all tensors must be contiguous CUDA fp32 on one device")
+    if not (step_state.is_cuda and step_state.dtype == torch.int64 and step_state.numel() >= 2 and step_state.device == dev):
+        raise RuntimeError("adam_step_capturable: step_state must be an int64[2] CUDA tensor on the parameters' device")
+    n = len(params)
+    numel = (ctypes.c_int64 * n)(*[p.numel() for p in params])
+    with torch.cuda.device(dev):
+        rc = lib.clica_adam_step_capturable(n, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs),
+                                            _ptr_array(exp_avg_sqs), numel, float(lr), float(beta1), float(beta2),
+                                            float(eps), step_state.data_ptr(), float(grad_scale), _stream_ptr(dev))
+        _lib.check(rc, "clica_adam_step_capturable")
+
+
+def invalidate_packed_weights():
+    """Drop every cached packed-weight buffer (the next encoder call re-packs from the live parameters)."""
+    _packed_cache.clear()

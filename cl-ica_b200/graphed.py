@@ -1,0 +1,143 @@
+"""GraphedTrainStep: the whole InfoNCE training step recorded once into a CUDA graph and replayed per step.
+
+The step is the unsupervised branch of the reference's ``train_step`` (``main_mlp.py:258-285``):
+
+    zero_grad -> z1_rec = h(z1), z2_rec = h(z2) -> z3_rec = roll(z1_rec, 1, 0) -> LpSimCLRLoss -> backward -> Adam.step
+
+with ``h = f o g`` (``main_mlp.py:313``).  At the reference's sizes the step is a chain of ~45 short kernels
+(0.9 ms of device time at n = 10, B = 6144) and the eager Python/autograd dispatch of that chain costs about as
+much again on the host.  Recording it once (``torch.cuda.graph``: device memory and streams are PyTorch's, every
+kernel is this library's) removes the host from the loop:
+
+* the (anchor, positive) batch is staged in ONE pinned host buffer ``[2B, n]``; the graph starts with its
+  host->device copy and ends with the device->host copy of ``(loss, pos_mean, neg_mean)`` into pinned memory
+  (``host_io=True``), so one replay is a complete step from host data to host scalars;
+* anchors and positives go through the encoder as one 2B-row batch (identical arithmetic per row);
+* Adam runs as ``FusedAdam(capturable=True)``: its step count lives on the device, so consecutive replays are
+  consecutive optimizer steps.
+
+Warm-up steps needed before capture are rolled back (parameters and optimizer state are restored), so a freshly
+built object has taken zero optimizer steps.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from . import functional as F
+from .optim import FusedAdam
+
+
+class GraphedTrainStep:
+    def __init__(self, f: torch.nn.Module, g: Optional[torch.nn.Module], criterion, batch_size: int, n_in: int,
+                 lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, host_io: bool = True,
+                 device: Optional[torch.device] = None, warmup: int = 3):
+        _lib.load()
+        params = [p for p in f.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("GraphedTrainStep: the encoder must live on a CUDA device (no CPU path)")
+        self.device = params[0].device if device is None else torch.device(device)
+        self.f, self.g, self.criterion = f, g, criterion
+        self.B, self.n = int(batch_size), int(n_in)
+        self.host_io = bool(host_io)
+        self.params = params
+        self.optimizer = FusedAdam(params, lr=lr, betas=betas, eps=eps, capturable=True)
+        dev = self.device
+        self.z_dev = torch.zeros((2 * self.B, self.n), dtype=torch.float32, device=dev)
+        self.out_dev = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.z_host = torch.zeros((2 * self.B, self.n), dtype=torch.float32).pin_memory() if host_io else None
+        self.out_host = torch.zeros(3, dtype=torch.float32).pin_memory() if host_io else None
+        self.stream = torch.cuda.Stream(dev)
+        self.launches_per_replay = 0
+        self.steps_taken = 0
+        self._capture(max(int(warmup), 1))
+
+    # the recorded body -------------------------------------------------------------------------------------
+    def _body(self):
+        if self.host_io:
+            self.z_dev.copy_(self.z_host, non_blocking=True)
+        self.optimizer.zero_grad(set_to_none=True)
+        x = self.z_dev if self.g is None else self.g(self.z_dev)
+        ab = self.f(x)
+        a, b = ab[:self.B], ab[self.B:]
+        total, _, parts = self.criterion(None, None, None, a, b, torch.roll(a, 1, 0))
+        total.backward()
+        self.optimizer.step()
+        torch.stack([total.detach(), parts[0].detach(), parts[1].detach()], out=self.out_dev)
+        if self.host_io:
+            self.out_host.copy_(self.out_dev, non_blocking=True)
+
+    def _capture(self, warmup):
+        lib = _lib.load()
+        dev = self.device
+        with torch.no_grad():
+            saved = [p.detach().clone() for p in self.params]
+        cur = torch.cuda.current_stream(dev)
+        self.stream.wait_stream(cur)
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            for _ in range(warmup):          # sizes every workspace / cuBLAS handle on the capture stream
+                self._body()
+            self.stream.synchronize()
+            F.invalidate_packed_weights()    # the weight re-pack must be part of the recording
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = lib.clica_launch_count(-1)
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self._body()
+            self.launches_per_replay = int(lib.clica_launch_count(-1) - n0)
+            # roll the warm-up back: parameters, moments and the device step count
+            with torch.no_grad():
+                for p, s in zip(self.params, saved):
+                    p.copy_(s)
+                for st in self.optimizer.state.values():
+                    st["exp_avg"].zero_()
+                    st["exp_avg_sq"].zero_()
+                for group in self.optimizer.param_groups:
+                    if group.get("_step_state") is not None:
+                        group["_step_state"].zero_()
+            self.stream.synchronize()
+        cur.wait_stream(self.stream)
+        torch.autograd.graph.increment_version(self.params)
+
+    # per-step API ----------------------------------------------------------------------------------------------
+    def stage(self, z1: torch.Tensor, z2: torch.Tensor) -> None:
+        """Put this step's (anchor, positive) latents where the graph reads them: host tensors go into the pinned
+        staging buffer (``host_io=True``), device tensors into the device-resident input."""
+        B = self.B
+        if z1.shape != (B, self.n) or z2.shape != (B, self.n):
+            raise RuntimeError(f"GraphedTrainStep: expected two [{B}, {self.n}] tensors, got {tuple(z1.shape)}, {tuple(z2.shape)}")
+        if z1.is_cuda != z2.is_cuda:
+            raise RuntimeError("GraphedTrainStep: z1 and z2 must both be host or both be device tensors")
+        if not z1.is_cuda:
+            if not self.host_io:
+                raise RuntimeError("GraphedTrainStep(host_io=False) takes device tensors")
+            self.z_host[:B].copy_(z1)
+            self.z_host[B:].copy_(z2)
+        else:
+            if self.host_io:
+                raise RuntimeError("GraphedTrainStep(host_io=True) takes host tensors (the graph copies them to the device)")
+            self.z_dev[:B].copy_(z1)
+            self.z_dev[B:].copy_(z2)
+
+    def replay(self) -> torch.Tensor:
+        """One training step on the staged inputs (asynchronous). Returns the device tensor
+        ``[loss, pos_mean, neg_mean]`` that the step overwrites."""
+        self.graph.replay()
+        self.steps_taken += 1
+        torch.autograd.graph.increment_version(self.params)     # the graph updated the parameters in place
+        return self.out_dev
+
+    def __call__(self, z1: Optional[torch.Tensor] = None, z2: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if z1 is not None:
+            self.stage(z1, z2)
+        return self.replay()
+
+    def step_host(self, z1: torch.Tensor, z2: torch.Tensor) -> Tuple[float, float, float]:
+        """Host tensors in, host floats out (what ``main_mlp.py:285`` reads with ``.item()``): stage, replay,
+        wait for the graph's own device->host copy."""
+        if not self.host_io:
+            raise RuntimeError("step_host needs host_io=True")
+        self.stage(z1, z2)
+        self.replay()
+        torch.cuda.current_stream(self.device).synchronize()
+        o = self.out_host
+        return float(o[0]), float(o[1]), float(o[2])

@@ -199,6 +199,15 @@ CLICA_API int clica_adam_step(int n, float* const* params, const float* const* g
                     float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1,
                     float beta2, float eps, int64_t step, float grad_scale, void* stream);
 
+/* Capturable variant (CUDA-graph replays of the whole training step): the step count lives on the device.
+ * step_state: 16-byte, 8-byte aligned device buffer { int64 step; float lr/(1-b1^t); float 1/sqrt(1-b2^t) },
+ * zero-initialised by the caller before the first step; each call advances it by one on the device (a
+ * one-thread kernel, same double-precision bias corrections as the host variant) and then applies the
+ * update, so replaying a captured graph performs consecutive Adam steps with no host-side state. */
+CLICA_API int clica_adam_step_capturable(int n, float* const* params, const float* const* grads,
+                    float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel, float lr,
+                    float beta1, float beta2, float eps, void* step_state, float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Launch accounting (bench.py's `gpu_launches` and per-kernel roofline numbers; no reference analogue).
  *   clica_launch_count(family)  kernels launched by this library in this process (family < 0: all)
