@@ -41,10 +41,23 @@ namespace {
 
 // ---- skinny-layer launchers (skinny.cuh) ----------------------------------------------------------------
 int launch_skinny_kin(const SkinnyKinParams& q, cudaStream_t st) {
-    const int grid = ceil_div(q.M, kSkRows);
+    const dim3 grid(ceil_div(q.M, kKinRows), ceil_div(q.N, kKinCols));
     LaunchScope ls(st, kFamGemmSimt);
     if (q.K <= 16) skinny_kin_kernel<16><<<grid, 256, 0, st>>>(q);
     else skinny_kin_kernel<48><<<grid, 256, 0, st>>>(q);
+    CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int launch_skinny_nout_small(const SkinnyNoutParams& q, cudaStream_t st) {
+    const size_t smem = nout_small_smem_bytes(q.N);
+    static bool attr = false;
+    if (!attr) {
+        CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)nout_small_smem_bytes(kNsMaxN)));
+        attr = true;
+    }
+    LaunchScope ls(st, kFamGemmSimt);
+    skinny_nout_small_kernel<<<ceil_div(q.M, kNsRows), 256, smem, st>>>(q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -66,15 +79,22 @@ int launch_skinny_nout(const SkinnyNoutParams& q, int sm_count, cudaStream_t st)
     return 0;
 }
 bool skinny_dw_ok(int N, int K) { return (size_t)kSkRows * (N + K + 1) * sizeof(float) <= 64 * 1024 && (size_t)N * (K + 1) <= 32768; }
-int launch_skinny_dw(const SkinnyDwParams& q, cudaStream_t st) {
+int launch_skinny_dw(const SkinnyDwParams& q, int sm_count, cudaStream_t st) {
     const size_t smem = (size_t)kSkRows * (q.N + q.K + 1) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_dw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
     LaunchScope ls(st, kFamGemmSimt);
-    skinny_dw_kernel<<<ceil_div(q.M, kSkRows), 256, smem, st>>>(q);
+    const int tiles = ceil_div(q.M, kSkRows);
+    if ((size_t)q.N * (q.K + 1) <= (size_t)kDwsMaxOut) {
+        const int grid = tiles < sm_count ? tiles : sm_count;
+        skinny_dw_small_kernel<<<grid, 256, smem, st>>>(q);
+    } else {
+        skinny_dw_kernel<<<tiles, 256, smem, st>>>(q);
+    }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -88,10 +108,11 @@ int simt_fwd(PlanesIn x, const float* W, int ldw, const float* b, PlanesOut y, i
         s.o_hi = y.hi; s.o_lo = y.lo; s.ldo = y.ld; s.M = M; s.N = N; s.K = K; s.epi = 0;
         return launch_skinny_kin(s, st);
     }
-    if (y.lo == nullptr && skinny_nout_ok(N, K)) {
+    if (y.lo == nullptr && (N <= kNsMaxN || skinny_nout_ok(N, K))) {
         SkinnyNoutParams s = {};
         s.x_hi = x.hi; s.x_lo = x.lo; s.ldx = x.ld; s.W = W; s.ldw = ldw; s.bias = b; s.out = y.hi; s.ldo = y.ld;
         s.slope = slope; s.M = M; s.N = N; s.K = K;
+        if (N <= kNsMaxN) return launch_skinny_nout_small(s, st);
         return launch_skinny_nout(s, sm_count, st);
     }
     SimtGemmParams q = {};
@@ -129,7 +150,7 @@ int simt_bwd_weight(PlanesIn dy, PlanesIn x, float* dW, int lddw, float* db, int
         SkinnyDwParams s = {};
         s.dy_hi = dy.hi; s.dy_lo = dy.lo; s.lddy = dy.ld; s.x_hi = x.hi; s.x_lo = x.lo; s.ldx = x.ld;
         s.dW = dW; s.lddw = lddw; s.db = db; s.M = M; s.N = N; s.K = K;
-        return launch_skinny_dw(s, st);
+        return launch_skinny_dw(s, sm_count, st);
     }
     const int tiles = ceil_div(N, kSBM) * ceil_div(K, kSBN);
     int splits = (2 * sm_count + tiles - 1) / tiles;

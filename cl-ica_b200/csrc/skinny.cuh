@@ -40,12 +40,27 @@ struct SkinnyDwParams {
 
 constexpr int kSkRows = 32;
 
+// ---- skinny_kin: small reduction dim ------------------------------------------------------------------------
+// CTA = 64 rows x 128 output columns; thread = (column group of 4, row slot of 8): float4 stores of whole
+// 512-byte row segments per warp, the B(k, 4 columns) slice of a thread lives in registers (KMAX <= 16) or is read
+// as one LDS.128 per k, x values are warp-broadcast shared-memory reads.
+constexpr int kKinRows = 64;
+constexpr int kKinCols = 128;
+
 template <int KMAX>
 __global__ void __launch_bounds__(256) skinny_kin_kernel(const SkinnyKinParams q) {
-    __shared__ float xs[kSkRows][KMAX];
+    __shared__ __align__(16) float Bs[KMAX][kKinCols];
+    __shared__ __align__(16) float xs[kKinRows][KMAX];
+    __shared__ float cs[kKinCols];
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * kSkRows;
-    for (int idx = tid; idx < kSkRows * KMAX; idx += 256) {       // columns K..KMAX-1 are zero-filled
+    const int row0 = blockIdx.x * kKinRows;
+    const int n0 = blockIdx.y * kKinCols;
+    for (int idx = tid; idx < KMAX * kKinCols; idx += 256) {
+        const int k = idx / kKinCols, c = idx - k * kKinCols;
+        const int n = n0 + c;
+        Bs[k][c] = (k < q.K && n < q.N) ? __ldg(q.B + (long long)k * q.b_sk + (long long)n * q.b_sn) : 0.f;
+    }
+    for (int idx = tid; idx < kKinRows * KMAX; idx += 256) {       // columns K..KMAX-1 are zero-filled
         const int r = idx / KMAX, k = idx - r * KMAX;
         const int m = row0 + r;
         float v = 0.f;
@@ -55,36 +70,222 @@ __global__ void __launch_bounds__(256) skinny_kin_kernel(const SkinnyKinParams q
         }
         xs[r][k] = v;
     }
+    if (tid < kKinCols) cs[tid] = 0.f;
     __syncthreads();
-    const int nrows = min(kSkRows, q.M - row0);
-    for (int n = tid; n < q.N; n += 256) {
-        float w[KMAX];
+    const int cg = tid & 31, rs = tid >> 5;
+    const int nb = n0 + 4 * cg;
+    const int nrows = min(kKinRows, q.M - row0);
+    if (nb < q.N) {
+        const int nv = min(4, q.N - nb);                       // valid columns of this group
+        const bool vec_o = (nv == 4) && ((q.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.o_hi) & 15u) == 0) &&
+                           (q.o_lo == nullptr || (reinterpret_cast<uintptr_t>(q.o_lo) & 15u) == 0);
+        const bool vec_a = (nv == 4) && q.aux && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15u) == 0);
+        float bias_v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (q.epi == 0 && q.bias) {
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) w[k] = (k < q.K) ? __ldg(q.B + k * q.b_sk + n * q.b_sn) : 0.f;
-        const float bias_v = (q.epi == 0 && q.bias) ? __ldg(q.bias + n) : 0.f;
-        float csum = 0.f;
-        for (int r = 0; r < nrows; ++r) {
-            float acc = 0.f;
+            for (int j = 0; j < 4; ++j) if (j < nv) bias_v[j] = __ldg(q.bias + nb + j);
+        }
+        float4 breg[KMAX <= 16 ? KMAX : 1];
+        if constexpr (KMAX <= 16) {
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) acc = fmaf(xs[r][k], w[k], acc);
-            const size_t m = (size_t)(row0 + r);
-            float v = acc;
-            if (q.epi == 0) {
-                v += bias_v;
-                v = v > 0.f ? v : v * q.slope;
-            } else if (q.aux) {
-                v *= (__ldg(q.aux + m * q.ldaux + n) > 0.f) ? 1.f : q.slope;
+            for (int k = 0; k < KMAX; ++k) breg[k] = *reinterpret_cast<const float4*>(&Bs[k][4 * cg]);
+        }
+        float csum[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = rs; r < nrows; r += 8) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k4 = 0; k4 < KMAX; k4 += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k4]);
+                const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    float4 b;
+                    if constexpr (KMAX <= 16) b = breg[k4 + kk];
+                    else b = *reinterpret_cast<const float4*>(&Bs[k4 + kk][4 * cg]);
+                    a[0] = fmaf(xk[kk], b.x, a[0]); a[1] = fmaf(xk[kk], b.y, a[1]);
+                    a[2] = fmaf(xk[kk], b.z, a[2]); a[3] = fmaf(xk[kk], b.w, a[3]);
+                }
             }
-            csum += v;
+            const size_t m = (size_t)(row0 + r);
+            if (q.epi == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a[j] += bias_v[j]; a[j] = a[j] > 0.f ? a[j] : a[j] * q.slope; }
+            } else if (q.aux) {
+                float mk[4] = {1.f, 1.f, 1.f, 1.f};
+                const float* ap = q.aux + m * q.ldaux + nb;
+                if (vec_a) {
+                    const float4 av = __ldg(reinterpret_cast<const float4*>(ap));
+                    mk[0] = av.x; mk[1] = av.y; mk[2] = av.z; mk[3] = av.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < nv) mk[j] = __ldg(ap + j);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[j] *= (mk[j] > 0.f) ? 1.f : q.slope;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) csum[j] += a[j];
+            float* oh = q.o_hi + m * q.ldo + nb;
             if (q.o_lo) {
-                const float h = round_to_tf32(v);
-                q.o_hi[m * q.ldo + n] = h;
-                q.o_lo[m * q.ldo + n] = round_to_tf32(v - h);
+                float* ol = q.o_lo + m * q.ldo + nb;
+                float h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { h[j] = round_to_tf32(a[j]); l[j] = round_to_tf32(a[j] - h[j]); }
+                if (vec_o) {
+                    *reinterpret_cast<float4*>(oh) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(ol) = make_float4(l[0], l[1], l[2], l[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < nv) { oh[j] = h[j]; ol[j] = l[j]; }
+                }
+            } else if (vec_o) {
+                *reinterpret_cast<float4*>(oh) = make_float4(a[0], a[1], a[2], a[3]);
             } else {
-                q.o_hi[m * q.ldo + n] = v;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < nv) oh[j] = a[j];
             }
         }
-        if (q.colsum) atomicAdd(q.colsum + n, csum);
+        if (q.colsum) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(&cs[4 * cg + j], csum[j]);
+        }
+    }
+    if (q.colsum) {
+        __syncthreads();
+        if (tid < kKinCols && n0 + tid < q.N) atomicAdd(q.colsum + n0 + tid, cs[tid]);
+    }
+}
+
+// ---- skinny_nout_small: output dim <= 16 ---------------------------------------------------------------------
+// CTA = 64 rows; X (hi + lo summed) and W are staged in shared memory in K-chunks of 128 with coalesced loads,
+// thread = one (row, n) output per item (n fastest: coalesced stores), up to 4 items per thread.
+constexpr int kNsRows = 64;
+constexpr int kNsKC = 128;
+constexpr int kNsMaxN = 16;
+constexpr int kNsItems = kNsRows * kNsMaxN / 256;
+inline size_t nout_small_smem_bytes(int N) { return (size_t)(kNsRows + N) * (kNsKC + 1) * sizeof(float); }
+
+static __global__ void __launch_bounds__(256) skinny_nout_small_kernel(const SkinnyNoutParams q) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int LD = kNsKC + 1;
+    float* xs = sm;                       // [kNsRows][LD]
+    float* ws = sm + kNsRows * LD;        // [N][LD]
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * kNsRows;
+    const int nrows = min(kNsRows, q.M - row0);
+    const int items = nrows * q.N;
+    float acc[kNsItems];
+#pragma unroll
+    for (int i = 0; i < kNsItems; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < q.K; k0 += kNsKC) {
+        const int kc = min(kNsKC, q.K - k0);
+        if (k0 > 0) __syncthreads();
+        for (int idx = tid; idx < kNsRows * kNsKC; idx += 256) {
+            const int r = idx / kNsKC, k = idx - r * kNsKC;
+            float v = 0.f;
+            if (r < nrows && k < kc) {
+                const size_t off = (size_t)(row0 + r) * q.ldx + k0 + k;
+                v = __ldg(q.x_hi + off);
+                if (q.x_lo) v += __ldg(q.x_lo + off);
+            }
+            xs[r * LD + k] = v;
+        }
+        for (int idx = tid; idx < q.N * kNsKC; idx += 256) {
+            const int n = idx / kNsKC, k = idx - n * kNsKC;
+            ws[n * LD + k] = (k < kc) ? __ldg(q.W + (size_t)n * q.ldw + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kNsItems; ++i) {
+            const int item = tid + 256 * i;
+            if (item < items) {
+                const int r = item / q.N, n = item - r * q.N;
+                const float* xr = xs + r * LD;
+                const float* wr = ws + n * LD;
+                float a0 = acc[i], a1 = 0.f;
+                int k = 0;
+                for (; k + 1 < kc; k += 2) { a0 = fmaf(xr[k], wr[k], a0); a1 = fmaf(xr[k + 1], wr[k + 1], a1); }
+                if (k < kc) a0 = fmaf(xr[k], wr[k], a0);
+                acc[i] = a0 + a1;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kNsItems; ++i) {
+        const int item = tid + 256 * i;
+        if (item < items) {
+            const int r = item / q.N, n = item - r * q.N;
+            float v = acc[i] + (q.bias ? __ldg(q.bias + n) : 0.f);
+            v = v > 0.f ? v : v * q.slope;
+            q.out[(size_t)(row0 + r) * q.ldo + n] = v;
+        }
+    }
+}
+
+// ---- skinny_dw_small: N * (K + 1) <= 2048 outputs ------------------------------------------------------------
+// Persistent over 32-row tiles: every thread keeps up to 8 outputs (n, k) in registers while its CTA walks its
+// tiles, then issues ONE atomic per output per CTA (the tile-at-a-time kernel below issues one per output per tile).
+constexpr int kDwsMaxOut = 2048;
+constexpr int kDwsItems = kDwsMaxOut / 256;
+
+static __global__ void __launch_bounds__(256) skinny_dw_small_kernel(const SkinnyDwParams q) {
+    extern __shared__ __align__(16) float sm[];
+    float* dys = sm;                                  // [kSkRows][N]
+    float* xs = sm + kSkRows * q.N;                   // [kSkRows][K + 1]
+    const int KK = q.K + 1;
+    const int total = q.N * KK;
+    float acc[kDwsItems];
+#pragma unroll
+    for (int i = 0; i < kDwsItems; ++i) acc[i] = 0.f;
+    const int ntiles = (q.M + kSkRows - 1) / kSkRows;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int row0 = t * kSkRows;
+        if (t != (int)blockIdx.x) __syncthreads();
+        for (int idx = threadIdx.x; idx < kSkRows * q.N; idx += 256) {
+            const int r = idx / q.N, n = idx - r * q.N;
+            const int m = row0 + r;
+            float v = 0.f;
+            if (m < q.M) {
+                v = __ldg(q.dy_hi + (size_t)m * q.lddy + n);
+                if (q.dy_lo) v += __ldg(q.dy_lo + (size_t)m * q.lddy + n);
+            }
+            dys[idx] = v;
+        }
+        for (int idx = threadIdx.x; idx < kSkRows * KK; idx += 256) {
+            const int r = idx / KK, k = idx - r * KK;
+            const int m = row0 + r;
+            float v = 0.f;
+            if (m < q.M) {
+                if (k < q.K) {
+                    v = __ldg(q.x_hi + (size_t)m * q.ldx + k);
+                    if (q.x_lo) v += __ldg(q.x_lo + (size_t)m * q.ldx + k);
+                } else {
+                    v = 1.f;
+                }
+            }
+            xs[idx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kDwsItems; ++i) {
+            const int o = threadIdx.x + 256 * i;
+            if (o < total) {
+                const int n = o / KK, k = o - n * KK;
+                float a = acc[i];
+#pragma unroll 8
+                for (int r = 0; r < kSkRows; ++r) a = fmaf(dys[r * q.N + n], xs[r * KK + k], a);
+                acc[i] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kDwsItems; ++i) {
+        const int o = threadIdx.x + 256 * i;
+        if (o < total) {
+            const int n = o / KK, k = o - n * KK;
+            if (k < q.K) atomicAdd(q.dW + (size_t)n * q.lddw + k, acc[i]);
+            else if (q.db) atomicAdd(q.db + n, acc[i]);
+        }
     }
 }
 

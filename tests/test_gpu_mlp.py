@@ -99,6 +99,39 @@ def test_encoder_stack_against_numpy_oracle(mode_name, n, M, cuda_device):
         assert _rel(bs[l].grad.cpu().numpy(), dbs[l]) <= tol, f"db{l}"
 
 
+@pytest.mark.parametrize("mode_name,tol", [("fp32", 2e-5), ("3xtf32", 2e-4)])
+def test_encoder_stack_n40(mode_name, tol, cuda_device):
+    """BASELINE config 3's encoder (n = 40: 40 -> 400 -> 2000 x4 -> 400 -> 40).  The first / last layers take the
+    KMAX = 48 skinny kernels; the 2000-wide tensor-core layers accumulate 63 k-blocks, where the tensor core's
+    truncating fp32 accumulator costs 3xTF32 a few 1e-5 (stated tolerance 2e-4; exact-fp32 mode 2e-5)."""
+    from clica_b200 import functional as F
+    from oracle import mlp_oracle
+    mode = MODES[mode_name][0]
+    n, M = 40, 384
+    rng = np.random.RandomState(40)
+    widths = [n, 10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n, n]
+    Wn = [(rng.uniform(-1, 1, size=(widths[i + 1], widths[i])) / np.sqrt(widths[i])).astype(np.float32) for i in range(7)]
+    bn = [(rng.uniform(-1, 1, size=(widths[i + 1],)) / np.sqrt(widths[i])).astype(np.float32) for i in range(7)]
+    xn = rng.randn(M, n).astype(np.float32)
+    xn = xn[_safe_rows(xn, Wn, bn)]
+    M = len(xn)
+    assert M >= 32
+    gyn = rng.randn(M, n).astype(np.float32)
+    Ws = [torch.tensor(w, device=cuda_device, requires_grad=True) for w in Wn]
+    bs = [torch.tensor(b, device=cuda_device, requires_grad=True) for b in bn]
+    x = torch.tensor(xn, device=cuda_device, requires_grad=True)
+    y = F.mlp_forward(x, Ws, bs, slope=0.01, mode=mode)
+    y.backward(torch.tensor(gyn, device=cuda_device))
+    y_ref, acts, pre = mlp_oracle.mlp_forward(xn, Wn, bn, slope=0.01)
+    dWs, dbs, dx = mlp_oracle.mlp_backward(gyn, Wn, acts, pre, slope=0.01, need_dx=True)
+    errs = {"y": _rel(y.detach().cpu().numpy(), y_ref), "dx": _rel(x.grad.cpu().numpy(), dx)}
+    for l in range(7):
+        errs[f"dW{l}"] = _rel(Ws[l].grad.cpu().numpy(), dWs[l])
+        errs[f"db{l}"] = _rel(bs[l].grad.cpu().numpy(), dbs[l])
+    print(f"n=40 {mode_name}: max rel err {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+    assert max(errs.values()) <= tol, errs
+
+
 def test_dropin_get_mlp_on_cuda_matches_torch_modules(cuda_device):
     """The FusedMLP returned by the drop-in get_mlp must agree with the same nn modules run by torch."""
     import sys
