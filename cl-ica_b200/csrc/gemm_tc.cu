@@ -32,6 +32,7 @@ namespace {
 constexpr int BM = 128, BK = 32;                       // BK fp32 = 128 bytes = one swizzle span; BN = 128 or 256 (template)
 constexpr int kTcThreads = 320;                          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
+constexpr int kPairDefault = 0;                          // CLICA_TC_PAIR default (1: CTA pairs, tcgen05 cta_group::2)
 constexpr size_t kEpiStageBytes = 8 * 4096;                 // one 32 x 32 fp32 staging block per epilogue warp
 
 struct TcKernelParams {
@@ -96,20 +97,70 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int CTAS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {   // executed by one warp of EACH CTA of the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
+template <int CTAS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if constexpr (CTAS == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CTAS == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {   // issued by the leader CTA only: M = 256 over the pair, each CTA's tensor core produces its 128 rows
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// ---- CTA-pair (cluster of 2) helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar_cluster_addr) {
     asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar_cluster_addr), "r"(x), "r"(y) : "memory");
+}
+// tcgen05.commit that arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -152,26 +203,39 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 // instruction descriptor: D fp32, A/B tf32, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n, int m = BM) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // one operand tile of a stage: K-major = one {32 x ROWS} box; MN-major = ROWS/32 boxes of {32 x 32}
-template <int ROWS>
-__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar) {
+template <int ROWS, int CTAS>
+__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar,
+                                             uint32_t bar_cluster) {
     if (!mn_major) {
-        tma_load_2d(dst, tm, k0, mn0, bar);
+        if constexpr (CTAS == 1) tma_load_2d(dst, tm, k0, mn0, bar);
+        else tma_load_2d_pair(dst, tm, k0, mn0, bar_cluster);
     } else {
 #pragma unroll
-        for (int j = 0; j < ROWS / 32; ++j) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
+        for (int j = 0; j < ROWS / 32; ++j) {
+            if constexpr (CTAS == 1) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
+            else tma_load_2d_pair(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar_cluster);
+        }
     }
 }
 
 // Persistent kernel: grid = min(#work items, #SMs); a work item is (split, n-tile, m-tile) with m fastest so that
 // CTAs running side by side share the B tile in L2.  The accumulator is double-buffered in TMEM (2 x BN columns),
 // so the epilogue of item i overlaps the main loop of item i+1; the smem ring runs continuously across items.
-template <int BN>
+//
+// CTAS == 2 (CTA pair, cluster of two CTAs on the two SMs of a TPC, tcgen05 cta_group::2): a work item is a
+// 256 x BN tile.  Each CTA loads ITS 128 rows of A and ITS half (BN/2 rows) of B -- the pair's tensor cores read the
+// other half of B from the peer's shared memory -- so a CTA pulls (128 + BN/2) operand rows per k-block from L2
+// instead of (128 + BN): the kernel is paced by L2->SM operand delivery (two fp32 planes per operand), not by the
+// tensor pipe.  Only the leader CTA (cluster rank 0) issues MMAs; its "stage full" barrier collects the TMA bytes of
+// both CTAs, tcgen05.commit multicasts "stage free" / "accumulator ready" to both, and the epilogue warps of both
+// CTAs (each drains its own 128 TMEM lanes) report to the leader's "accumulator free" barrier.
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -185,25 +249,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[BN];
 
-    constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
+    constexpr int BNL = BN / CTAS;                         // B rows this CTA loads per k-block
+    constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BNL * BK * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+    const int unit_id = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;     // a unit = one CTA or one CTA pair
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzled tiles need 1024-byte alignment
     const int nplanes = (q.nterms == 3) ? 2 : 1;
     const uint32_t stage_bytes = (uint32_t)nplanes * (kABytes + kBBytes);
-    const int num_m = (q.Mo + BM - 1) / BM, num_n = (q.No + BN - 1) / BN;
+    const int num_m = (q.Mo + BM * CTAS - 1) / (BM * CTAS), num_n = (q.No + BN - 1) / BN;
     const int total = num_m * num_n * q.splits;
     long long* const tm = q.timing ? q.timing + (size_t)blockIdx.x * 8 : nullptr;
     if (tm && threadIdx.x == 0) tm[0] = clock64();
 
     if (warp == 0 && lane == 0) {
+        // pair mode: the leader's full barrier expects the TMA bytes of BOTH CTAs (one arrive.expect_tx by the leader's
+        // producer; the peer's loads complete_tx on it); the leader's accumulator-free barrier takes the 8 epilogue
+        // warps of each CTA
         for (int s = 0; s < q.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8 * CTAS); }
         fence_barrier_init();
     }
     constexpr uint32_t kTmemCols = (BN <= 128) ? 256u : 512u;       // two accumulators; allocations are powers of two
-    if (warp == 1) tmem_alloc(&tmem_slot, kTmemCols);
+    if (warp == 1) tmem_alloc<CTAS>(&tmem_slot, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();        // the peer's barriers are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
     if (tm && threadIdx.x == 0) tm[1] = clock64();
@@ -212,38 +283,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         if (lane == 0) {
             // ===== TMA producer =====
             uint32_t it = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int m0 = (w % num_m) * BM;
+            for (int w = unit_id; w < total; w += num_units) {
+                const int m0 = (w % num_m) * (BM * CTAS) + (int)cta_rank * BM;       // this CTA's 128 rows of A
                 const int rest = w / num_m;
-                const int n0 = (rest % num_n) * BN;
+                const int n0 = (rest % num_n) * BN + (int)cta_rank * BNL;            // this CTA's share of B
                 const int kb0 = (rest / num_n) * q.kb_per_split;
                 const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)q.stages;
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    uint32_t fb = 0;                                 // pair mode: the LEADER's full barrier
+                    if constexpr (CTAS == 1) {
+                        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    } else {
+                        // the peer's loads for this phase cannot start before its own empty barrier flipped, i.e. before
+                        // the leader's full barrier finished the previous phase: a complete_tx that overtakes this
+                        // expect_tx only drives the (signed) tx-count negative for a moment
+                        fb = mapa_u32(smem_u32(&full_bar[s]), 0u);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes * CTAS);
+                    }
                     const uint32_t sa = tiles + s * stage_bytes;
                     const uint32_t sb = sa + nplanes * kABytes;
                     const int k0 = kb * BK;
-                    load_operand<BM>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s]);
-                    if (nplanes == 2) load_operand<BM>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s]);
-                    load_operand<BN>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s]);
-                    if (nplanes == 2) load_operand<BN>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s]);
+                    load_operand<BM, CTAS>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s], fb);
+                    if (nplanes == 2) load_operand<BM, CTAS>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s], fb);
+                    load_operand<BNL, CTAS>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s], fb);
+                    if (nplanes == 2) load_operand<BNL, CTAS>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s], fb);
                     if (tm && it == 0) tm[2] = clock64();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, BN);
+        if (lane == 0 && cta_rank == 0) {
+            // ===== MMA issuer (pair mode: the leader CTA drives both tensor cores) =====
+            const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, BN, BM * CTAS);
             const uint32_t a_step = q.a_mn ? 1024u : 32u, b_step = q.b_mn ? 1024u : 32u;   // bytes per K = 8 step
             const uint32_t a_lbo = q.a_mn ? q.mn_lbo : 16u, b_lbo = q.b_mn ? q.mn_lbo : 16u;
             const uint32_t a_sbo = q.a_mn ? q.mn_sbo : 1024u, b_sbo = q.b_mn ? q.mn_sbo : 1024u;
             const uint32_t a_lt = q.a_mn ? q.mn_lt : 2u, b_lt = q.b_mn ? q.mn_lt : 2u;
             uint32_t it = 0, tile_iter = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
+            for (int w = unit_id; w < total; w += num_units, ++tile_iter) {
                 const int rest = w / num_m;
                 const int kb0 = (rest / num_n) * q.kb_per_split;
                 const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
@@ -268,16 +348,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                         if (nplanes == 2) {
                             const uint64_t dal = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
                             const uint64_t dbl = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-                            umma_tf32(tmem_acc, dal, dbh, idesc, first);   // small terms first
-                            umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
-                            umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                            umma_tf32<CTAS>(tmem_acc, dal, dbh, idesc, first);   // small terms first
+                            umma_tf32<CTAS>(tmem_acc, dah, dbl, idesc, 1u);
+                            umma_tf32<CTAS>(tmem_acc, dah, dbh, idesc, 1u);
                         } else {
-                            umma_tf32(tmem_acc, dah, dbh, idesc, first);
+                            umma_tf32<CTAS>(tmem_acc, dah, dbh, idesc, first);
                         }
                     }
-                    umma_commit(&empty_bar[s]);            // stage reusable once these MMAs have read it
+                    // stage reusable once these MMAs have read it (pair mode: in both CTAs)
+                    if constexpr (CTAS == 1) umma_commit(&empty_bar[s]); else umma_commit_pair(&empty_bar[s]);
                 }
-                umma_commit(&tmem_full_bar[as]);           // accumulator complete
+                // accumulator complete (pair mode: each CTA's epilogue drains its own 128 TMEM lanes)
+                if constexpr (CTAS == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_pair(&tmem_full_bar[as]);
                 if (tm) tm[4] = clock64();
             }
         }
@@ -315,8 +397,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             return t;
         };
         uint32_t tile_iter = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
-            const int m0 = (w % num_m) * BM;
+        for (int w = unit_id; w < total; w += num_units, ++tile_iter) {
+            const int m0 = (w % num_m) * (BM * CTAS) + (int)cta_rank * BM;
             const int n0 = ((w / num_m) % num_n) * BN;
             const uint32_t as = tile_iter & 1u;
             const int row = m0 + wq * 32 + lane;
@@ -432,7 +514,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             // this warp has read its share of the accumulator: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (lane == 0) {
+                if constexpr (CTAS == 1) mbar_arrive(&tmem_empty_bar[as]);
+                else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0u));
+            }
             if (tm && etid == 0) tm[6] = clock64();
         }
         if (lane == 0) bulk_wait_all0();      // the staging buffer must outlive the last bulk store
@@ -440,10 +525,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();    // the peer's shared memory / TMEM stay alive until both are done
     if (tm && threadIdx.x == 0) tm[7] = clock64();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc<CTAS>(tmem_base, kTmemCols);
     }
 }
 
@@ -544,28 +630,31 @@ int get_tensor_map(const float* ptr, int rows, int cols, int ld, int box_rows, b
 // BM * BN * 4 * planes output bytes (weighted x4: write / reduce traffic drains slower than loads stream), and
 // a persistent CTA works through ceil(items / #SMs) items.  Pick the (BN, splits) with the shortest makespan;
 // ties go to the wider tile (less operand traffic per flop).
+// ctas == 2: CTA pairs -- a unit of work is a 256 x bn tile on one of sm_count / 2 pairs, and each CTA of the pair
+// pulls (BM + bn / 2) operand rows per k-block.
 struct TilePlan { int bn; int splits; };
-TilePlan plan_tiles(int Mo, int No, int kb_total, int sm_count, bool split_k) {
+TilePlan plan_tiles(int Mo, int No, int kb_total, int sm_count, bool split_k, int ctas) {
     const int forced = env_int("CLICA_TC_BN", 0);
     const int widths[3] = {256, 192, 128};
     TilePlan best = {256, 1};
     double best_cost = 1e300;
+    const int units = sm_count / ctas > 0 ? sm_count / ctas : 1;
     for (int i = 0; i < 3; ++i) {
         const int bn = widths[i];
         if (forced == 128 || forced == 192 || forced == 256) { if (bn != forced) continue; }
         else if (bn > 128 && No <= bn - 64) continue;           // a narrower tile already covers the whole output
-        const long long tiles = (long long)ceil_div(Mo, BM) * ceil_div(No, bn);
+        const long long tiles = (long long)ceil_div(Mo, BM * ctas) * ceil_div(No, bn);
         const int max_splits = split_k ? (kb_total / 4 > 0 ? kb_total / 4 : 1) : 1;
         for (int sp = 1; sp <= max_splits; ++sp) {
             const int kb_per = ceil_div(kb_total, sp);
             const int sp_eff = ceil_div(kb_total, kb_per);
             if (sp_eff != sp) continue;                         // same work division as a smaller split count
             const long long items = tiles * sp;
-            const long long waves = (items + sm_count - 1) / sm_count;
-            const double item_cost = (double)kb_per * (BM + bn) + 4.0 * bn * (split_k ? 2.0 : 1.0);
+            const long long waves = (items + units - 1) / units;
+            const double item_cost = (double)kb_per * (BM + bn / ctas) + 4.0 * bn * (split_k ? 2.0 : 1.0);
             const double cost = (double)waves * item_cost;
             if (cost < best_cost * 0.999) { best_cost = cost; best.bn = bn; best.splits = sp; }
-            if (items > 8LL * sm_count) break;
+            if (items > 8LL * units) break;
         }
     }
     return best;
@@ -587,13 +676,16 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
     const int nterms = g.A.lo ? 3 : 1;
     const int nplanes = (nterms == 3) ? 2 : 1;
-    const TilePlan tp = plan_tiles(g.Mo, g.No, ceil_div(g.Kr, BK), sm_count, g.epi == kTcAtomic && g.allow_split_k);
+    // CTA pairs (tcgen05 cta_group::2) whenever the output has more than one 128-row tile; CLICA_TC_PAIR=0 disables
+    const int ctas = (env_int("CLICA_TC_PAIR", kPairDefault) != 0 && g.Mo > BM && sm_count >= 2) ? 2 : 1;
+    const TilePlan tp = plan_tiles(g.Mo, g.No, ceil_div(g.Kr, BK), sm_count, g.epi == kTcAtomic && g.allow_split_k, ctas);
     const int bn = tp.bn;
+    const int bnl = bn / ctas;                                  // B rows one CTA loads per k-block
     CUtensorMap tAh, tAl, tBh, tBl, tOh, tOl;
     int rc;
     // storage shape of each operand: K-major [MN rows][Kr cols] (box = tile rows); MN-major [Kr rows][MN cols] (box 32 rows)
     const int a_rows = g.a_mn_major ? g.Kr : g.Mo, a_cols = g.a_mn_major ? g.Mo : g.Kr, a_box = g.a_mn_major ? BK : BM;
-    const int b_rows = g.b_mn_major ? g.Kr : g.No, b_cols = g.b_mn_major ? g.No : g.Kr, b_box = g.b_mn_major ? BK : bn;
+    const int b_rows = g.b_mn_major ? g.Kr : g.No, b_cols = g.b_mn_major ? g.No : g.Kr, b_box = g.b_mn_major ? BK : bnl;
     if ((rc = get_tensor_map(g.A.hi, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAh))) return rc;
     if ((rc = get_tensor_map(g.B.hi, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBh))) return rc;
     if (nterms == 3) {
@@ -615,7 +707,7 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     q.Mo = g.Mo; q.No = g.No;
     q.kb_total = ceil_div(g.Kr, BK);
     q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms;
-    const size_t stage_bytes = (size_t)nplanes * (BM + bn) * BK * 4;
+    const size_t stage_bytes = (size_t)nplanes * (BM + bnl) * BK * 4;
     const size_t smem_cap = 227 * 1024 - 2048;                  // static shared memory (barriers, bias slice) + slack
     const size_t smem_fixed = 1024 + kEpiStageBytes;            // alignment slack + 8 x 4 KB epilogue staging
     q.stages = (int)((smem_cap - smem_fixed) / stage_bytes);
@@ -631,7 +723,7 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
         const char* tp = getenv("CLICA_TC_TIMING_PTR");
         q.timing = tp ? (long long*)(uintptr_t)strtoull(tp, nullptr, 0) : nullptr;
     }
-    const int tiles = ceil_div(g.Mo, BM) * ceil_div(g.No, bn);
+    const int tiles = ceil_div(g.Mo, BM * ctas) * ceil_div(g.No, bn);
     int splits = tp.splits;
     q.kb_per_split = ceil_div(q.kb_total, splits);
     splits = ceil_div(q.kb_total, q.kb_per_split);
@@ -640,18 +732,36 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         const int max_dyn = (int)smem_cap;
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
         attr_set = true;
     }
     const int total = tiles * splits;
-    const int grid = total < sm_count ? total : sm_count;
+    const int units = sm_count / ctas;
+    const int grid = (total < units ? total : units) * ctas;
     {
         LaunchScope ls(st, kFamGemmTc);
-        if (bn == 256) gemm_tc_kernel<256><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
-        else if (bn == 192) gemm_tc_kernel<192><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
-        else gemm_tc_kernel<128><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
+        if (ctas == 1) {
+            if (bn == 256) gemm_tc_kernel<256, 1><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
+            else if (bn == 192) gemm_tc_kernel<192, 1><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
+            else gemm_tc_kernel<128, 1><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t e;
+            if (bn == 256) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, 2>, tAh, tAl, tBh, tBl, tOh, tOl, q);
+            else if (bn == 192) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<192, 2>, tAh, tAl, tBh, tBl, tOh, tOl, q);
+            else e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, 2>, tAh, tAl, tBh, tBl, tOh, tOl, q);
+            CLICA_CUDA_OK(e);
+        }
     }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;

@@ -90,8 +90,10 @@ int launch_skinny_dw(const SkinnyDwParams& q, int sm_count, cudaStream_t st) {
     LaunchScope ls(st, kFamGemmSimt);
     const int tiles = ceil_div(q.M, kSkRows);
     if ((size_t)q.N * (q.K + 1) <= (size_t)kDwsMaxOut) {
-        const int grid = tiles < sm_count ? tiles : sm_count;
-        skinny_dw_small_kernel<<<grid, 256, smem, st>>>(q);
+        // two tiles per CTA (halves the atomics of the tile-at-a-time kernel) unless that leaves > 2 CTAs per SM
+        int per_cta = ceil_div(tiles, 2 * sm_count);
+        if (per_cta < 2) per_cta = 2;
+        skinny_dw_small_kernel<<<ceil_div(tiles, per_cta), 256, smem, st>>>(q);
     } else {
         skinny_dw_kernel<<<tiles, 256, smem, st>>>(q);
     }

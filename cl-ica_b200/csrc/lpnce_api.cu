@@ -43,18 +43,47 @@ __global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v_loss = 0.f, v_pos = 0.f, v_lse = 0.f;
     if (i < q.B) {
+        // loads are issued in independent batches of 8 (a load -> use loop pays one memory latency per iteration)
         float ps = 0.f;
         const float* a = q.z1 + (size_t)i * q.ld1;
         const float* b = q.z2 + (size_t)i * q.ld2;
-        for (int c = 0; c < q.d; ++c) ps += abs_pow(a[c] - b[c], q.p);
+        for (int c0 = 0; c0 < q.d; c0 += 8) {
+            float av[8], bv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = c0 + u < q.d;
+                av[u] = ok ? __ldg(a + c0 + u) : 0.f;
+                bv[u] = ok ? __ldg(b + c0 + u) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ps += abs_pow(av[u] - bv[u], q.p);     // |0|^p = 0 for the padding
+        }
         const float coef = kLog2e / q.tau;
-        float M = q.part_m[i];
-        for (int sidx = 1; sidx < q.nsplit; ++sidx) M = fmaxf(M, q.part_m[(size_t)sidx * q.part_stride + i]);
         const float xp = -ps * coef;
-        if (q.include_pos) M = fmaxf(M, xp);
-        float S = q.include_pos ? exp2f(xp - M) : 0.f;
-        for (int sidx = 0; sidx < q.nsplit; ++sidx)
-            S += q.part_s[(size_t)sidx * q.part_stride + i] * exp2f(q.part_m[(size_t)sidx * q.part_stride + i] - M);
+        float M = q.include_pos ? xp : -INFINITY;
+        float S = 0.f;
+        // pass 1: row maximum over the split partials; pass 2 (partials now in L1/L2): rescaled sum, fixed order
+        for (int s0 = 0; s0 < q.nsplit; s0 += 8) {
+            float pm[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                pm[u] = (s0 + u < q.nsplit) ? q.part_m[(size_t)(s0 + u) * q.part_stride + i] : -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) M = fmaxf(M, pm[u]);
+        }
+        if (q.include_pos) S = exp2f(xp - M);
+        for (int s0 = 0; s0 < q.nsplit; s0 += 8) {
+            float pm[8], psum[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = s0 + u < q.nsplit;
+                pm[u] = ok ? q.part_m[(size_t)(s0 + u) * q.part_stride + i] : 0.f;
+                psum[u] = ok ? q.part_s[(size_t)(s0 + u) * q.part_stride + i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (s0 + u < q.nsplit) S += psum[u] * exp2f(pm[u] - M);
+        }
         const float ls = log2f(S);
         q.rowstat[i] = make_float2(M, ls);
         float l = (M + ls) * kLn2;
@@ -82,14 +111,22 @@ __global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) 
         is_last = (atomicAdd(q.counter, 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {
+        // the last block adds the per-block sums in block order: thread t takes blocks t, t + 256, ... (parallel
+        // loads), thread 0 then adds the 256 per-thread sums in thread order -- a fixed order, so deterministic
+        __shared__ double fin[3][256];
         __threadfence();
-        volatile double* bs = q.block_sums;
+        const volatile double* bs = q.block_sums;
         double s0 = 0, s1 = 0, s2 = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) { s0 += bs[3 * b]; s1 += bs[3 * b + 1]; s2 += bs[3 * b + 2]; }
-        q.scalars[0] = (float)(s0 / q.B);
-        q.scalars[1] = (float)(s1 / q.B);
-        q.scalars[2] = (float)(s2 / q.B);
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) { s0 += bs[3 * b]; s1 += bs[3 * b + 1]; s2 += bs[3 * b + 2]; }
+        fin[0][threadIdx.x] = s0; fin[1][threadIdx.x] = s1; fin[2][threadIdx.x] = s2;
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0;
+            const int nb = gridDim.x < 256 ? (int)gridDim.x : 256;
+            for (int k = 0; k < nb; ++k) t += fin[threadIdx.x][k];
+            q.scalars[threadIdx.x] = (float)(t / q.B);
+        }
     }
 }
 

@@ -55,20 +55,39 @@ __global__ void __launch_bounds__(256) skinny_kin_kernel(const SkinnyKinParams q
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * kKinRows;
     const int n0 = blockIdx.y * kKinCols;
-    for (int idx = tid; idx < KMAX * kKinCols; idx += 256) {
-        const int k = idx / kKinCols, c = idx - k * kKinCols;
-        const int n = n0 + c;
-        Bs[k][c] = (k < q.K && n < q.N) ? __ldg(q.B + (long long)k * q.b_sk + (long long)n * q.b_sn) : 0.f;
-    }
-    for (int idx = tid; idx < kKinRows * KMAX; idx += 256) {       // columns K..KMAX-1 are zero-filled
-        const int r = idx / KMAX, k = idx - r * KMAX;
-        const int m = row0 + r;
-        float v = 0.f;
-        if (m < q.M && k < q.K) {
-            v = __ldg(q.x_hi + (size_t)m * q.ldx + k);
-            if (q.x_lo) v += __ldg(q.x_lo + (size_t)m * q.ldx + k);
+    // staging: every thread first issues ALL of its global loads (independent, in flight together), then stores --
+    // a load -> store loop would pay one full memory latency per iteration
+    {
+        constexpr int NB = KMAX * kKinCols / 256;            // 8 (KMAX 16) or 24 (KMAX 48) elements per thread
+        float v[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int idx = tid + 256 * u;
+            const int k = idx / kKinCols, c = idx - k * kKinCols;
+            const int n = n0 + c;
+            v[u] = (k < q.K && n < q.N) ? __ldg(q.B + (long long)k * q.b_sk + (long long)n * q.b_sn) : 0.f;
         }
-        xs[r][k] = v;
+        constexpr int NX = kKinRows * KMAX / 256;            // 4 or 12
+        float xh[NX], xl[NX];
+#pragma unroll
+        for (int u = 0; u < NX; ++u) {                       // columns K..KMAX-1 are zero-filled
+            const int idx = tid + 256 * u;
+            const int r = idx / KMAX, k = idx - r * KMAX;
+            const int m = row0 + r;
+            const bool ok = (m < q.M && k < q.K);
+            xh[u] = ok ? __ldg(q.x_hi + (size_t)m * q.ldx + k) : 0.f;
+            xl[u] = (ok && q.x_lo) ? __ldg(q.x_lo + (size_t)m * q.ldx + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int idx = tid + 256 * u;
+            Bs[idx / kKinCols][idx % kKinCols] = v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < NX; ++u) {
+            const int idx = tid + 256 * u;
+            xs[idx / KMAX][idx % KMAX] = xh[u] + xl[u];
+        }
     }
     if (tid < kKinCols) cs[tid] = 0.f;
     __syncthreads();
@@ -180,19 +199,58 @@ static __global__ void __launch_bounds__(256) skinny_nout_small_kernel(const Ski
     for (int k0 = 0; k0 < q.K; k0 += kNsKC) {
         const int kc = min(kNsKC, q.K - k0);
         if (k0 > 0) __syncthreads();
-        for (int idx = tid; idx < kNsRows * kNsKC; idx += 256) {
-            const int r = idx / kNsKC, k = idx - r * kNsKC;
-            float v = 0.f;
-            if (r < nrows && k < kc) {
-                const size_t off = (size_t)(row0 + r) * q.ldx + k0 + k;
-                v = __ldg(q.x_hi + off);
-                if (q.x_lo) v += __ldg(q.x_lo + off);
+        {   // all global loads of the chunk first (independent), then the shared-memory stores
+            constexpr int NV = kNsRows * kNsKC / 4 / 256;    // 8 float4 per thread
+            const bool vec = ((q.ldx & 3) == 0) && ((k0 & 3) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(q.x_hi) & 15u) == 0) &&
+                             (q.x_lo == nullptr || (reinterpret_cast<uintptr_t>(q.x_lo) & 15u) == 0);
+            float4 vh[NV], vl[NV];
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int idx = tid + 256 * u;
+                const int r = idx / (kNsKC / 4), k = 4 * (idx - r * (kNsKC / 4));
+                vh[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                vl[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nrows && k < kc) {
+                    const size_t off = (size_t)(row0 + r) * q.ldx + k0 + k;
+                    if (vec && k + 3 < kc) {
+                        vh[u] = __ldg(reinterpret_cast<const float4*>(q.x_hi + off));
+                        if (q.x_lo) vl[u] = __ldg(reinterpret_cast<const float4*>(q.x_lo + off));
+                    } else {
+                        vh[u].x = __ldg(q.x_hi + off);
+                        if (k + 1 < kc) vh[u].y = __ldg(q.x_hi + off + 1);
+                        if (k + 2 < kc) vh[u].z = __ldg(q.x_hi + off + 2);
+                        if (k + 3 < kc) vh[u].w = __ldg(q.x_hi + off + 3);
+                        if (q.x_lo) {
+                            vl[u].x = __ldg(q.x_lo + off);
+                            if (k + 1 < kc) vl[u].y = __ldg(q.x_lo + off + 1);
+                            if (k + 2 < kc) vl[u].z = __ldg(q.x_lo + off + 2);
+                            if (k + 3 < kc) vl[u].w = __ldg(q.x_lo + off + 3);
+                        }
+                    }
+                }
             }
-            xs[r * LD + k] = v;
-        }
-        for (int idx = tid; idx < q.N * kNsKC; idx += 256) {
-            const int n = idx / kNsKC, k = idx - n * kNsKC;
-            ws[n * LD + k] = (k < kc) ? __ldg(q.W + (size_t)n * q.ldw + k0 + k) : 0.f;
+            constexpr int NW = (kNsMaxN * kNsKC + 255) / 256;  // 8 weights per thread
+            float wv[NW];
+#pragma unroll
+            for (int u = 0; u < NW; ++u) {
+                const int idx = tid + 256 * u;
+                const int n = idx / kNsKC, k = idx - n * kNsKC;
+                wv[u] = (n < q.N && k < kc) ? __ldg(q.W + (size_t)n * q.ldw + k0 + k) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int idx = tid + 256 * u;
+                const int r = idx / (kNsKC / 4), k = 4 * (idx - r * (kNsKC / 4));
+                float* d = xs + r * LD + k;
+                d[0] = vh[u].x + vl[u].x; d[1] = vh[u].y + vl[u].y; d[2] = vh[u].z + vl[u].z; d[3] = vh[u].w + vl[u].w;
+            }
+#pragma unroll
+            for (int u = 0; u < NW; ++u) {
+                const int idx = tid + 256 * u;
+                const int n = idx / kNsKC, k = idx - n * kNsKC;
+                if (n < q.N) ws[n * LD + k] = wv[u];
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -241,29 +299,40 @@ static __global__ void __launch_bounds__(256) skinny_dw_small_kernel(const Skinn
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int row0 = t * kSkRows;
         if (t != (int)blockIdx.x) __syncthreads();
-        for (int idx = threadIdx.x; idx < kSkRows * q.N; idx += 256) {
-            const int r = idx / q.N, n = idx - r * q.N;
-            const int m = row0 + r;
-            float v = 0.f;
-            if (m < q.M) {
-                v = __ldg(q.dy_hi + (size_t)m * q.lddy + n);
-                if (q.dy_lo) v += __ldg(q.dy_lo + (size_t)m * q.lddy + n);
+        // batches of 8 independent loads per thread (hi and lo), then the shared-memory stores
+        for (int base = threadIdx.x; base < kSkRows * q.N; base += 256 * 8) {
+            float vh[8], vl[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + 256 * u;
+                const int r = idx / q.N, n = idx - r * q.N;
+                const int m = row0 + r;
+                const bool ok = (idx < kSkRows * q.N) && (m < q.M);
+                vh[u] = ok ? __ldg(q.dy_hi + (size_t)m * q.lddy + n) : 0.f;
+                vl[u] = (ok && q.dy_lo) ? __ldg(q.dy_lo + (size_t)m * q.lddy + n) : 0.f;
             }
-            dys[idx] = v;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + 256 * u;
+                if (idx < kSkRows * q.N) dys[idx] = vh[u] + vl[u];
+            }
         }
-        for (int idx = threadIdx.x; idx < kSkRows * KK; idx += 256) {
-            const int r = idx / KK, k = idx - r * KK;
-            const int m = row0 + r;
-            float v = 0.f;
-            if (m < q.M) {
-                if (k < q.K) {
-                    v = __ldg(q.x_hi + (size_t)m * q.ldx + k);
-                    if (q.x_lo) v += __ldg(q.x_lo + (size_t)m * q.ldx + k);
-                } else {
-                    v = 1.f;
-                }
+        for (int base = threadIdx.x; base < kSkRows * KK; base += 256 * 8) {
+            float vh[8], vl[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + 256 * u;
+                const int r = idx / KK, k = idx - r * KK;
+                const int m = row0 + r;
+                const bool ok = (idx < kSkRows * KK) && (m < q.M);
+                vh[u] = !ok ? 0.f : (k < q.K ? __ldg(q.x_hi + (size_t)m * q.ldx + k) : 1.f);
+                vl[u] = (ok && k < q.K && q.x_lo) ? __ldg(q.x_lo + (size_t)m * q.ldx + k) : 0.f;
             }
-            xs[idx] = v;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + 256 * u;
+                if (idx < kSkRows * KK) xs[idx] = vh[u] + vl[u];
+            }
         }
         __syncthreads();
 #pragma unroll

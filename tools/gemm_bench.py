@@ -15,8 +15,10 @@ def timed(fn, reps=20):
     ms = (ctypes.c_float * 7)(); n = (ctypes.c_int * 7)()
     lib.clica_prof_collect(ms, n); lib.clica_prof_enable(0)
     return ms[3] / max(n[3], 1) * 1e3, ms[6] / reps * 1e3     # us per tc-gemm launch, misc us per call
-shapes = [(6144, 100, 500), (6144, 500, 500), (6144, 500, 100), (8192, 2000, 2000), (8192, 400, 2000)]
-for mode_name, mode in (("3xtf32", 0), ("tf32", 1)):
+shapes = [(12288, 100, 500), (12288, 500, 500), (12288, 500, 100), (16384, 2000, 2000), (16384, 400, 2000)]
+modes = (("3xtf32", 0), ("tf32", 1)) if "--all-modes" in sys.argv else (("3xtf32", 0),)
+print("CLICA_TC_PAIR =", os.environ.get("CLICA_TC_PAIR", "(default)"), flush=True)
+for mode_name, mode in modes:
     for (M, K, N) in shapes:
         x = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
         y = torch.empty(M, N, device=dev); dy = torch.randn(M, N, device=dev); dx = torch.empty(M, K, device=dev)
