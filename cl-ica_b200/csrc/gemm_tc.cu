@@ -139,6 +139,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
