@@ -32,7 +32,7 @@ namespace {
 constexpr int BM = 128, BK = 32;                       // BK fp32 = 128 bytes = one swizzle span; BN = 128 or 256 (template)
 constexpr int kTcThreads = 320;                          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
-constexpr int kPairDefault = 0;                          // CLICA_TC_PAIR default (1: CTA pairs, tcgen05 cta_group::2)
+constexpr int kPairDefault = 1;                          // CLICA_TC_PAIR default (1: CTA pairs, tcgen05 cta_group::2)
 constexpr size_t kEpiStageBytes = 8 * 4096;                 // one 32 x 32 fp32 staging block per epilogue warp
 
 struct TcKernelParams {
@@ -210,6 +210,15 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n, int m 
 }
 
 // one operand tile of a stage: K-major = one {32 x ROWS} box; MN-major = ROWS/32 boxes of {32 x 32}
+// MMA width of the n-tile that starts `rem` columns before the edge of the output: a ragged last tile issues a
+// narrower MMA (multiples of 32 columns per CTA) instead of multiplying TMA zero-fill
+template <int BN, int CTAS>
+__device__ __forceinline__ int tile_width(int rem) {
+    constexpr int G = 32 * CTAS;
+    const int w = (rem + G - 1) / G * G;
+    return w < BN ? w : BN;
+}
+
 template <int ROWS, int CTAS>
 __device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar,
                                              uint32_t bar_cluster) {
@@ -287,7 +296,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             for (int w = unit_id; w < total; w += num_units) {
                 const int m0 = (w % num_m) * (BM * CTAS) + (int)cta_rank * BM;       // this CTA's 128 rows of A
                 const int rest = w / num_m;
-                const int n0 = (rest % num_n) * BN + (int)cta_rank * BNL;            // this CTA's share of B
+                const int nt0 = (rest % num_n) * BN;
+                const int n0 = nt0 + (int)cta_rank * (tile_width<BN, CTAS>(q.No - nt0) / CTAS);   // this CTA's share of B
                 const int kb0 = (rest / num_n) * q.kb_per_split;
                 const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -318,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0 && cta_rank == 0) {
             // ===== MMA issuer (pair mode: the leader CTA drives both tensor cores) =====
-            const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, BN, BM * CTAS);
+
             const uint32_t a_step = q.a_mn ? 1024u : 32u, b_step = q.b_mn ? 1024u : 32u;   // bytes per K = 8 step
             const uint32_t a_lbo = q.a_mn ? q.mn_lbo : 16u, b_lbo = q.b_mn ? q.mn_lbo : 16u;
             const uint32_t a_sbo = q.a_mn ? q.mn_sbo : 1024u, b_sbo = q.b_mn ? q.mn_sbo : 1024u;
@@ -332,6 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 mbar_wait(&tmem_empty_bar[as], ((tile_iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + as * (uint32_t)BN;
+                const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, tile_width<BN, CTAS>(q.No - (rest % num_n) * BN), BM * CTAS);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)q.stages;
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
@@ -678,7 +689,15 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     const int nterms = g.A.lo ? 3 : 1;
     const int nplanes = (nterms == 3) ? 2 : 1;
     // CTA pairs (tcgen05 cta_group::2) whenever the output has more than one 128-row tile; CLICA_TC_PAIR=0 disables
-    const int ctas = (env_int("CLICA_TC_PAIR", kPairDefault) != 0 && g.Mo > BM && sm_count >= 2) ? 2 : 1;
+    //   1: always;  2: only where the isolated per-shape timings favoured pairs (tools/gemm_bench.py): weight-gradient
+    //   GEMMs always, forward GEMMs wider than one tile, masked backward-data GEMMs with >= 32 k-blocks
+    const int pair_mode = env_int("CLICA_TC_PAIR", kPairDefault);
+    bool pair_ok = pair_mode != 0 && g.Mo > BM && sm_count >= 2;
+    if (pair_ok && pair_mode == 2) {
+        if (g.epi == kTcBiasAct) pair_ok = g.No > 128;
+        else if (g.epi == kTcMask) pair_ok = ceil_div(g.Kr, BK) >= 32;
+    }
+    const int ctas = pair_ok ? 2 : 1;
     const TilePlan tp = plan_tiles(g.Mo, g.No, ceil_div(g.Kr, BK), sm_count, g.epi == kTcAtomic && g.allow_split_k, ctas);
     const int bn = tp.bn;
     const int bnl = bn / ctas;                                  // B rows one CTA loads per k-block
