@@ -390,10 +390,24 @@ def run_ours(args):
         }
         if gemm_ms >= loss_ms:
             ach = work["enc_flops"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+            mma_per_product = 3 if args.gemm_mode == "3xtf32" else 1
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")     # from the committed ncu --set full capture
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    tj = json.load(fh)
+                if tj.get("workload") == args.workload and world == 1 and args.gemm_mode == "3xtf32":
+                    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
             roofline = {"bound": "tensor", "kernel": "encoder GEMMs (" + ("tcgen05 " + args.gemm_mode if fam_ms["gemm_tc"] > fam_ms["gemm_simt"] else "CUDA-core fp32") + ")",
                         "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": peaks["source"] + " bf16 sustained; tf32 MMA peak is half of it and 3xtf32 issues 3 MMAs per product",
+                        # the same achieved number in units of the instructions the mode actually issues: tf32 MMAs run
+                        # at half the bf16 rate and the fp32-accurate 3xtf32 mode spends 3 of them per product
+                        "tf32_mma_tflops_issued": ach * mma_per_product,
+                        "frac_of_tf32_peak": ach * mma_per_product / (peaks["bf16_tflops_sustained"] / 2.0),
+                        "launches_per_step": fam_n["gemm_tc"] + fam_n["gemm_simt"],
+                        "avg_launch_us": gemm_ms * 1e3 / max(fam_n["gemm_tc"] + fam_n["gemm_simt"], 1),
                         "share_of_step": gemm_ms / max(kernels["sum_ms"], 1e-9)}
         else:
             ach = work["loss_bytes"] / (loss_ms * 1e-3) / 1e9
