@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="time the eager step instead of the CUDA-graph replay (single GPU)")
     ap.set_defaults(graph=os.environ.get("CLICA_GRAPH", "1") != "0")
+    ap.add_argument("--graph-multi", dest="graph_multi", action="store_true",
+                    help="multi-GPU: record the sharded step (incl. its NCCL collectives) into the CUDA graph too")
+    ap.add_argument("--no-graph-multi", dest="graph_multi", action="store_false")
+    ap.set_defaults(graph_multi=os.environ.get("CLICA_GRAPH_MULTI", "0") != "0")
     return ap.parse_args()
 
 
@@ -258,9 +262,10 @@ def run_ours(args):
     # replayed -- no host work between the ~45 kernels of a step.  CLICA_GRAPH=0 times the eager step instead.
     step_mode = "eager"
     graphed = None
-    if world == 1 and args.graph:
+    if args.graph and (world == 1 or args.graph_multi):
         from clica_b200.graphed import GraphedTrainStep
-        graphed = GraphedTrainStep(f, g, crit, B_local, n, lr=1e-4, host_io=False)
+        graphed = GraphedTrainStep(f, g, crit, B_local, n, lr=1e-4, host_io=False,
+                                   group=(dist.group.WORLD if world > 1 else None))
         graphed.stage(z1_d, z2_d)
         step_mode = "cuda_graph"
 
@@ -354,14 +359,15 @@ def run_ours(args):
 
     e2e_eager_ms = time_e2e(step_e2e_eager)
     e2e_ms, e2e_mode = e2e_eager_ms, "eager drop-in modules (as main_mlp.py runs them)"
-    if world == 1 and args.graph:
+    if args.graph and (world == 1 or args.graph_multi):
         # public API for a host-fed loop: GraphedTrainStep(host_io=True).step_host(z1_host, z2_host) stages the
         # host latents in pinned memory; the graph copies them to the device, runs the step and copies
         # (loss, pos_mean, neg_mean) back; step_host waits for that copy and returns Python floats
         from clica_b200.graphed import GraphedTrainStep
         torch.manual_seed(0)
         f3 = encoders.get_mlp(n, n, [10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n]).to(dev)
-        graphed_io = GraphedTrainStep(f3, g, crit, B_local, n, lr=1e-4, host_io=True)
+        graphed_io = GraphedTrainStep(f3, g, crit, B_local, n, lr=1e-4, host_io=True,
+                                      group=(dist.group.WORLD if world > 1 else None))
         e2e_ms = time_e2e(lambda: graphed_io.step_host(z1_h, z2_h))
         e2e_mode = "GraphedTrainStep.step_host (CUDA graph incl. H2D of the batch and D2H of the loss scalars)"
     e2e_value = B_global / (e2e_ms * 1e-3)

@@ -18,6 +18,10 @@ kernel is this library's) removes the host from the loop:
 
 Warm-up steps needed before capture are rolled back (parameters and optimizer state are restored), so a freshly
 built object has taken zero optimizer steps.
+
+Multi-GPU (``group`` given, one process per GPU): the recorded step is the row-sharded one of ``sharded.py`` -- the
+NCCL all-gathers of the encoder outputs / row statistics and the all-reduce of the parameter gradients are captured
+into the graph with the kernels (every rank records and replays the same sequence).
 """
 from typing import Optional, Tuple
 
@@ -31,7 +35,7 @@ from .optim import FusedAdam
 class GraphedTrainStep:
     def __init__(self, f: torch.nn.Module, g: Optional[torch.nn.Module], criterion, batch_size: int, n_in: int,
                  lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, host_io: bool = True,
-                 device: Optional[torch.device] = None, warmup: int = 3):
+                 device: Optional[torch.device] = None, warmup: int = 3, group=None):
         _lib.load()
         params = [p for p in f.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
@@ -41,6 +45,11 @@ class GraphedTrainStep:
         self.B, self.n = int(batch_size), int(n_in)
         self.host_io = bool(host_io)
         self.params = params
+        self.group = group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
         self.optimizer = FusedAdam(params, lr=lr, betas=betas, eps=eps, capturable=True)
         dev = self.device
         self.z_dev = torch.zeros((2 * self.B, self.n), dtype=torch.float32, device=dev)
@@ -60,8 +69,16 @@ class GraphedTrainStep:
         x = self.z_dev if self.g is None else self.g(self.z_dev)
         ab = self.f(x)
         a, b = ab[:self.B], ab[self.B:]
-        total, _, parts = self.criterion(None, None, None, a, b, torch.roll(a, 1, 0))
-        total.backward()
+        if self.world > 1:
+            from . import sharded
+            c = self.criterion
+            total, _, parts = sharded.sharded_lp_infonce(a, b, float(c.p), float(c.tau), float(c.alpha),
+                                                         bool(c.simclr_compatibility_mode), self.group)
+            total.backward()
+            sharded.allreduce_grads(self.params, self.group)
+        else:
+            total, _, parts = self.criterion(None, None, None, a, b, torch.roll(a, 1, 0))
+            total.backward()
         self.optimizer.step()
         torch.stack([total.detach(), parts[0].detach(), parts[1].detach()], out=self.out_dev)
         if self.host_io:
@@ -81,7 +98,10 @@ class GraphedTrainStep:
             F.invalidate_packed_weights()    # the weight re-pack must be part of the recording
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.clica_launch_count(-1)
-            with torch.cuda.graph(self.graph, stream=self.stream):
+            # NCCL's watchdog thread polls CUDA events while the collectives are being recorded: only this thread's
+            # calls may be policed during a multi-GPU capture
+            mode = "thread_local" if self.world > 1 else "global"
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode=mode):
                 self._body()
             self.launches_per_replay = int(lib.clica_launch_count(-1) - n0)
             # roll the warm-up back: parameters, moments and the device step count

@@ -38,6 +38,29 @@ for (n, B, p) in [(10, 2048, 2), (5, 1024, 1), (40, 1024, 3)]:
     if rank == 0:
         print(f"n={n} B={B} p={p} world={world}: loss sharded {loss.item():.7f} single {tot.item():.7f}  max grad err / max grad = {err:.2e}", flush=True)
     assert abs(loss.item() - tot.item()) <= 5e-6 * max(1.0, abs(tot.item())) and err <= 5e-4, (loss.item(), tot.item(), err)
+# the CUDA-graph sharded step (NCCL collectives recorded into the graph) follows the eager sharded trajectory
+if os.environ.get("CLICA_CHECK_GRAPH", "1") != "0":
+    import copy
+    from clica_b200.graphed import GraphedTrainStep
+    from clica_b200.optim import FusedAdam
+    n, B, p, lrate = 10, 2048, 2, 1e-3
+    torch.manual_seed(0)
+    f_g = encoders.get_mlp(n, n, [10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n]).to(dev)
+    f_e = copy.deepcopy(f_g)
+    g = synth.build_mixing(n, 3, seed=0).to(dev)
+    crit = losses.LpSimCLRLoss(p=p, tau=1.0, simclr_compatibility_mode=True)
+    Bl = B // world
+    step = GraphedTrainStep(f_g, g, crit, Bl, n, lr=lrate, host_io=False, group=dist.group.WORLD)
+    opt = FusedAdam(f_e.parameters(), lr=lrate)
+    for it in range(3):
+        z1, z2 = synth.synth_latents(B, n, "sphere", seed=20 + it)
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        z1l, z2l = z1[sl].to(dev), z2[sl].to(dev)
+        out = step(z1l, z2l).clone()
+        le, parts = sharded.sharded_train_step(f_e, g, opt, z1l, z2l, p, 1.0, 0.5)
+        if rank == 0:
+            print(f"graphed sharded step {it}: loss {out[0].item():.7f} eager {le.item():.7f}", flush=True)
+        assert abs(out[0].item() - le.item()) <= 1e-4 * max(1.0, abs(le.item())), (out, le)
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
