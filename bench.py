@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--graph-multi", dest="graph_multi", action="store_true",
                     help="multi-GPU: record the sharded step (incl. its NCCL collectives) into the CUDA graph too")
     ap.add_argument("--no-graph-multi", dest="graph_multi", action="store_false")
-    ap.set_defaults(graph_multi=os.environ.get("CLICA_GRAPH_MULTI", "0") != "0")
+    ap.set_defaults(graph_multi=os.environ.get("CLICA_GRAPH_MULTI", "1") != "0")
     return ap.parse_args()
 
 
@@ -262,11 +262,29 @@ def run_ours(args):
     # replayed -- no host work between the ~45 kernels of a step.  CLICA_GRAPH=0 times the eager step instead.
     step_mode = "eager"
     graphed = None
+    watchdog = None
     if args.graph and (world == 1 or args.graph_multi):
         from clica_b200.graphed import GraphedTrainStep
+        if world > 1:
+            # recording NCCL collectives into a graph cannot be abandoned in-process: if it wedges, fail fast and
+            # loudly instead of sitting in the launcher's timeout (CLICA_GRAPH_MULTI=0 selects the eager sharded step)
+            import threading
+
+            def _wedged():
+                sys.stderr.write("bench.py: multi-GPU CUDA-graph capture did not finish within 150 s; "
+                                 "rerun with CLICA_GRAPH_MULTI=0\n")
+                sys.stderr.flush()
+                os._exit(17)
+            watchdog = threading.Timer(150.0, _wedged)
+            watchdog.daemon = True
+            watchdog.start()
         graphed = GraphedTrainStep(f, g, crit, B_local, n, lr=1e-4, host_io=False,
                                    group=(dist.group.WORLD if world > 1 else None))
         graphed.stage(z1_d, z2_d)
+        graphed.replay()
+        torch.cuda.synchronize()
+        if watchdog is not None:
+            watchdog.cancel()
         step_mode = "cuda_graph"
 
     def step_device():
@@ -442,6 +460,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        if graphed is not None:
+            # communicators whose collectives live in instantiated CUDA graphs do not tear down cleanly (the
+            # process-group destructor waits on work the graphs still reference): every rank is done, leave
+            barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
