@@ -104,6 +104,45 @@ def cpu_baseline_run(wl, steps, warmup, rows=0, budget_s=25.0):
                 ms_per_step=dt * 1e3, rows=rows)
 
 
+def torch_eager_gpu_run(wl, dev, steps=5, warmup=2):
+    """The reference's torch formulation (oracle.torch_port.train_step: materialised B x B x d, cuBLAS fp32 encoder,
+    torch.optim.Adam) on the SAME GPU -- the kernel-to-beat baseline of SURVEY.md 8(d).  Baseline only; a failure
+    (e.g. out of memory at a large sweep point) is reported as null."""
+    import torch
+    from oracle import torch_port as tp
+    n, B, p, tau = wl["n"], wl["B"], wl["p"], wl["tau"]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False          # the reference's default: true fp32 matmuls
+        torch.manual_seed(0)
+        f = tp.build_encoder(n).to(dev)
+        g = tp.build_mixing(n, 3, seed=0).to(dev)
+        opt = torch.optim.Adam(f.parameters(), lr=1e-4)
+        z1, z2 = tp.synth_latents(B, n, wl["space"], seed=0)
+        z1, z2 = z1.to(dev), z2.to(dev)
+        for _ in range(warmup):
+            tp.train_step(f, g, opt, z1, z2, p, tau)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tp.train_step(f, g, opt, z1, z2, p, tau)         # ends with .item() like main_mlp.py:285
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / steps
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        return dict(value=B / dt, unit="pairs/s", ms_per_step=dt * 1e3, steps=steps, peak_mem_gb=peak_gb,
+                    what="oracle/torch_port.train_step = the reference's eager torch formulation on this GPU "
+                         "(fp32 cuBLAS, TF32 off, B x B x d materialised), full batch")
+    except Exception as exc:                                   # baseline only
+        return dict(value=None, error=repr(exc)[:200])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        try:
+            del f, g, opt, z1, z2
+        except Exception:
+            pass
+        torch.cuda.empty_cache()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -114,8 +153,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "positive-pairs/sec", "value": res["value"], "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "n": wl["n"], "batch": wl["B"], "p": wl["p"], "tau": wl["tau"],
-                   "device": "host CPU"},
+        # same workload keys as the CUDA arm's line (the sample is described in cpu_baseline.sample)
+        "config": {"workload": wl["desc"], "n": wl["n"], "batch_per_gpu": wl["B"], "global_batch": wl["B"],
+                   "p": wl["p"], "tau": wl["tau"], "parallelism": "host CPU threads (torch intra-op)"},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -439,10 +479,11 @@ def run_ours(args):
                         "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                         "traffic": None, "peak_source": peaks["source"],
                         "share_of_step": loss_ms / max(kernels["sum_ms"], 1e-9)}
-        cpu = None
+        cpu, eager_gpu = None, None
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_baseline_run(wl, steps=3, warmup=1, rows=args.cpu_sample_rows, budget_s=20.0)
             cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            eager_gpu = torch_eager_gpu_run(wl, dev)
         line = {
             "metric": "positive-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
@@ -456,7 +497,8 @@ def run_ours(args):
                     "eager_dropin_value": B_global / (e2e_eager_ms * 1e-3)},
             "step_mode": step_mode,
             "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
-            "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "loss": loss_value,
+            "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "torch_eager_gpu_baseline": eager_gpu, "loss": loss_value,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
