@@ -100,6 +100,23 @@ def loss_cases():
                                      alpha=0.5, compat=True, pow=True, roll=False)
     z1, z2 = pair(1, 10)
     cases["single_row"] = dict(z1=z1, z2=z2, p=2, tau=1.0, alpha=0.5, compat=True, pow=True, roll=True)
+    # --- added after the first GPU pass (drawn AFTER the cases above, so those stay bit-identical) ---
+    # real (non-integer) exponent and an integer exponent without a dedicated kernel (--p 5 is CLI-reachable)
+    z1, z2 = pair(45, 9, scale=0.8)
+    cases["indep_p2p5_generic"] = dict(z1=z1, z2=z2, z3=(rng.randn(61, 9) * 0.8).astype(np.float32), p=2.5, tau=0.8,
+                                       alpha=0.5, compat=True, pow=True, roll=False)
+    z1, z2 = pair(52, 10, scale=0.6)
+    cases["roll_p5_generic_cpupin"] = dict(z1=z1, z2=z2, p=5, tau=1.0, alpha=0.5, compat=True, pow=True, roll=True)
+    # wide feature vectors (BASELINE config 5 sweeps d = 128; the kernels split a pair over 2 / 4 / 8 lanes)
+    z1, z2 = pair(48, 128, scale=0.25)
+    cases["roll_p2_d128_wide"] = dict(z1=z1, z2=z2, p=2, tau=1.0, alpha=0.5, compat=True, pow=True, roll=True)
+    z1, z2 = pair(36, 200, scale=0.05)
+    cases["indep_p1_d200_wide"] = dict(z1=z1, z2=z2, z3=(rng.randn(70, 200) * 0.05).astype(np.float32), p=1, tau=2.0,
+                                       alpha=0.5, compat=True, pow=True, roll=False)
+    # row / column counts that straddle the kernels' 64-row and 128-column tiles
+    z1, z2 = pair(131, 10)
+    cases["indep_p3_ragged_tiles"] = dict(z1=z1, z2=z2, z3=rng.randn(259, 10).astype(np.float32), p=3, tau=1.5,
+                                          alpha=0.5, compat=True, pow=True, roll=False)
     return cases
 
 

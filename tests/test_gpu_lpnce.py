@@ -48,7 +48,9 @@ def _check(out, ref, roll, grad_tol=GRAD_TOL):
         assert np.abs(out["g3"] - ref["g3"]).max() <= grad_tol * gmax
 
 
-@pytest.mark.parametrize("name", [n for n in golden_loss_cases() if n != "nopow_p2"])
+# "*_cpupin" cases pin the CPU oracle only (e.g. p = 5: an integer exponent on the generic ex2/lg2 kernels, whose GPU
+# tolerance has not been measured yet); everything else runs on the GPU
+@pytest.mark.parametrize("name", [n for n in golden_loss_cases() if n != "nopow_p2" and not n.endswith("_cpupin")])
 def test_golden_vectors_from_the_reference(name, cuda_device):
     g = load_golden("lpnce_" + name)
     roll = bool(g["roll"])
@@ -56,7 +58,8 @@ def test_golden_vectors_from_the_reference(name, cuda_device):
                bool(g["compat"]), cuda_device, gl=g["gl"] if "gl" in g else None, roll=roll)
     ref = {k[:-3]: g[k] for k in g if k.endswith("_64")}
     ref["loss_mean"], ref["pos_mean"], ref["neg_mean"] = float(ref["loss_mean"]), float(ref["pos_mean"]), float(ref["neg_mean"])
-    _check(out, ref, roll)
+    generic = float(g["p"]) not in (1.0, 2.0, 3.0, 4.0)          # real exponents go through ex2/lg2.approx
+    _check(out, ref, roll, grad_tol=3e-5 if generic else GRAD_TOL)
 
 
 def test_pow_false_is_refused_not_approximated(cuda_device):

@@ -50,7 +50,9 @@ def test_torch_port_matches_reference_fp32(name):
     a = torch.tensor(g["z1"], requires_grad=True)
     b = torch.tensor(g["z2"], requires_grad=True)
     n = torch.roll(a, 1, 0) if roll else torch.tensor(g["z3"], requires_grad=True)
-    mean, per_item, parts = torch_port.lp_infonce(a, b, n, int(g["p"]), float(g["tau"]),
+    pexp = float(g["p"])
+    pexp = int(pexp) if pexp == int(pexp) else pexp          # the CLI passes ints; 2.5 pins the real-exponent path
+    mean, per_item, parts = torch_port.lp_infonce(a, b, n, pexp, float(g["tau"]),
                                                   float(g["alpha"]), bool(g["compat"]),
                                                   bool(g["pow"]))
     if "gl" in g:
