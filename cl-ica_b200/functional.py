@@ -340,3 +340,53 @@ def adam_step_capturable(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2,
 def invalidate_packed_weights():
     """Drop every cached packed-weight buffer (the next encoder call re-packs from the live parameters)."""
     _packed_cache.clear()
+
+
+# ---- frozen mixing network (EXPERIMENTAL: see include/clica.h, clica_mixing_fwd) ---------------------------
+def mixing_plan(g):
+    """(weights, slope) when ``g`` is the frozen mixing stack of invertible_network_utils.py:87-123 -- bias-free
+    square ``nn.Linear`` layers with one LeakyReLU slope in between, nothing requiring grad -- else None."""
+    from torch import nn
+    if not isinstance(g, nn.Sequential) or len(g) == 0:
+        return None
+    weights, slope, expect_linear = [], None, True
+    for m in g:
+        if expect_linear:
+            if not isinstance(m, nn.Linear) or m.bias is not None or m.weight.requires_grad:
+                return None
+            if m.weight.shape[0] != m.weight.shape[1] or (weights and m.weight.shape != weights[0].shape):
+                return None
+            weights.append(m.weight)
+        else:
+            if not isinstance(m, nn.LeakyReLU):
+                return None
+            s = float(m.negative_slope)
+            if slope is not None and s != slope:
+                return None
+            slope = s
+        expect_linear = not expect_linear
+    if expect_linear or not weights:          # must end on a Linear
+        return None
+    n = weights[0].shape[0]
+    if len(weights) > 8 or n > 48 or len(weights) * n * n * 4 > 48 * 1024:
+        return None
+    return weights, (0.2 if slope is None else slope)
+
+
+def mixing_forward(x, weights, slope):
+    """y = W_{L-1} lrelu( ... lrelu(W_0 x)) for frozen weights; no autograd graph is recorded (forward only)."""
+    lib = _lib.load()
+    x = _as_rows(x, "mixing input")
+    n = weights[0].shape[0]
+    if x.shape[1] != n:
+        raise RuntimeError(f"mixing_forward: input has {x.shape[1]} features, the mixing layers are {n} x {n}")
+    for W in weights:
+        if not (W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and W.device == x.device):
+            raise RuntimeError("mixing_forward: weights must be contiguous CUDA fp32 tensors on the input's device")
+    dev = x.device
+    with torch.cuda.device(dev):
+        y = torch.empty((x.shape[0], n), dtype=torch.float32, device=dev)
+        rc = lib.clica_mixing_fwd(x.data_ptr(), _ld(x), _ptr_array([W.detach() for W in weights]), len(weights), n,
+                                  x.shape[0], float(slope), y.data_ptr(), n, _stream_ptr(dev))
+        _lib.check(rc, "clica_mixing_fwd")
+    return y

@@ -23,6 +23,7 @@ Multi-GPU (``group`` given, one process per GPU): the recorded step is the row-s
 NCCL all-gathers of the encoder outputs / row statistics and the all-reduce of the parameter gradients are captured
 into the graph with the kernels (every rank records and replays the same sequence).
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -50,6 +51,10 @@ class GraphedTrainStep:
         if group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(group)
+        # EXPERIMENTAL (not yet run on a GPU, off by default): the frozen mixing net as one fused kernel
+        self._mix = None
+        if g is not None and os.environ.get("CLICA_FUSED_MIXING", "0") == "1":
+            self._mix = F.mixing_plan(g)
         self.optimizer = FusedAdam(params, lr=lr, betas=betas, eps=eps, capturable=True)
         dev = self.device
         self.z_dev = torch.zeros((2 * self.B, self.n), dtype=torch.float32, device=dev)
@@ -66,7 +71,12 @@ class GraphedTrainStep:
         if self.host_io:
             self.z_dev.copy_(self.z_host, non_blocking=True)
         self.optimizer.zero_grad(set_to_none=True)
-        x = self.z_dev if self.g is None else self.g(self.z_dev)
+        if self.g is None:
+            x = self.z_dev
+        elif self._mix is not None:
+            x = F.mixing_forward(self.z_dev, *self._mix)       # one kernel instead of L GEMMs + L-1 activations
+        else:
+            x = self.g(self.z_dev)
         ab = self.f(x)
         a, b = ab[:self.B], ab[self.B:]
         if self.world > 1:

@@ -209,6 +209,19 @@ CLICA_API int clica_adam_step_capturable(int n, float* const* params, const floa
                     float beta1, float beta2, float eps, void* step_state, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Frozen mixing network g of h = f o g (main_mlp.py:313), forward only.
+ *                                   replaces  the nn.Sequential of invertible_network_utils.py:87-123
+ *                                   (construct_invertible_mlp: L bias-free n x n Linear layers with
+ *                                   LeakyReLU(slope) in between) for CUDA fp32 inputs: one kernel instead
+ *                                   of L cuBLAS launches + L-1 elementwise launches.
+ *   x [M, n] (ld ldx), W[l] = the l-th layer's [n, n] weight (out x in, contiguous), y [M, n] (ld ldy).
+ *   Supported: 1 <= L <= 8, n <= 48, L*n*n*4 <= 48 KB.  EXPERIMENTAL in round 1: written after the round's
+ *   GPU budget was spent, not yet run on a GPU; nothing calls it unless CLICA_FUSED_MIXING=1.
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API int clica_mixing_fwd(const float* x, int ldx, const float* const* W, int L, int n, int M, float slope,
+                     float* y, int ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Launch accounting (bench.py's `gpu_launches` and per-kernel roofline numbers; no reference analogue).
  *   clica_launch_count(family)  kernels launched by this library in this process (family < 0: all)
  *   clica_prof_enable(on)       when on, every launch scope is bracketed by CUDA events on its stream
