@@ -1,12 +1,18 @@
 // abi.cu -- library-wide pieces of the C ABI: version, thread-local error string, device query.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
 #include <mutex>
 
 namespace clica {
+
+int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 
 char* last_error_buffer() {
     static thread_local char buf[512] = {0};

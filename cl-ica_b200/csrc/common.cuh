@@ -62,6 +62,8 @@ struct LaunchScope {
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// integer environment switch, read at every call (cheap; lets tests toggle experimental paths in-process)
+int env_flag(const char* name, int dflt);   // defined in abi.cu
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- device helpers ------------------------------------------------------------------------------

@@ -37,6 +37,7 @@ struct FinParams {
     int B; int M; int d; float p; float tau; float alpha; int include_pos;
     float* loss_i; float* lse; float* pos; float2* rowstat; float* scalars;
     double* block_sums; int* counter;
+    const float* z3; int ld3; int fast;   // EXPERIMENTAL fast forward: negatives, for the underflow fallback
 };
 
 __global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) {
@@ -83,6 +84,25 @@ __global__ void __launch_bounds__(256) lpnce_finalize_kernel(const FinParams q) 
 #pragma unroll
             for (int u = 0; u < 8; ++u)
                 if (s0 + u < q.nsplit) S += psum[u] * exp2f(pm[u] - M);
+        }
+        if (q.fast && !(S >= 0x1p-80f)) {
+            // fast forward (reference point 0): this row's soft-max sum is so small that terms flushed to zero could
+            // matter (or everything underflowed).  Recompute it robustly: maximum first, then the re-scaled sum.
+            float mx = q.include_pos ? xp : -INFINITY;
+            for (int j = 0; j < q.M; ++j) {
+                const float* c3 = q.z3 + (size_t)j * q.ld3;
+                float D = 0.f;
+                for (int c = 0; c < q.d; ++c) D += abs_pow(__ldg(a + c) - __ldg(c3 + c), q.p);
+                mx = fmaxf(mx, -D * coef);
+            }
+            float ssum = q.include_pos ? exp2f(xp - mx) : 0.f;
+            for (int j = 0; j < q.M; ++j) {
+                const float* c3 = q.z3 + (size_t)j * q.ld3;
+                float D = 0.f;
+                for (int c = 0; c < q.d; ++c) D += abs_pow(__ldg(a + c) - __ldg(c3 + c), q.p);
+                ssum += exp2f(-D * coef - mx);
+            }
+            M = mx; S = ssum;
         }
         const float ls = log2f(S);
         q.rowstat[i] = make_float2(M, ls);
@@ -349,6 +369,7 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
     q.coef = kLog2e / tau; q.pg = p;
     q.tiles_per_split = pl.tiles_per_split; q.flat16 = is_flat16(z3, ld3, d, sh);
     q.part_m = w.part_m; q.part_s = w.part_s; q.part_stride = B; q.counter = w.counter;
+    q.fast = env_flag("CLICA_LPNCE_FAST", 0) != 0;        // EXPERIMENTAL, off by default
     { LaunchScope ls(st, kFamLossFwd); rc = dispatch_fwd(p_code(p), sh, q, dim3(pl.row_tiles, pl.nsplit, 1), st); }
     if (rc) return rc;
 
@@ -358,6 +379,7 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
     f.alpha = alpha; f.include_pos = include_pos;
     f.loss_i = loss_i; f.lse = lse; f.pos = pos; f.rowstat = (float2*)rowstat; f.scalars = scalars3;
     f.block_sums = w.block_sums; f.counter = w.counter;
+    f.z3 = z3; f.ld3 = ld3; f.fast = q.fast;
     { LaunchScope ls(st, kFamLossAux); lpnce_finalize_kernel<<<ceil_div(B, 256), 256, 0, st>>>(f); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;

@@ -59,6 +59,7 @@ struct FwdParams {
     int tiles_per_split; int flat16;
     float* part_m; float* part_s; int part_stride;   // [nsplit][part_stride]
     int* counter;                        // zeroed here for the finalize kernel's last-block reduction
+    int fast;                            // EXPERIMENTAL: fixed reference point 0 (see lpnce_fwd_kernel, FAST)
 };
 
 // Row statistics of the forward, per anchor: (m2, ls) = (reference maximum of the log2-domain logits,
@@ -223,7 +224,12 @@ __device__ __forceinline__ void load_pair_rows(float2 (&bb)[2 * DP], const float
 }
 
 // ================================ forward ==========================================================
-template <int P, int DP, int R, int CW, int F>
+// FAST (EXPERIMENTAL, off unless CLICA_LPNCE_FAST=1; written after round 1's GPU budget was spent): every logit is
+// -D*coef <= 0, so exp2 can never overflow and the running reference point can simply be 0: no per-pair maximum, vote
+// or re-scaling (about a quarter of the instructions of the inner loop at d = 10).  What is lost is protection
+// against UNDERflow of a whole row (all logits < -126); the finalize kernel detects such rows (sum < 2^-80, where
+// flushed terms could matter) and recomputes them with a robust two-pass loop.
+template <int P, int DP, int R, int CW, int F, bool FAST>
 __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) {
     constexpr int RW = kWarps / CW;
     constexpr int RPW = 32 / F;                // rows per warp per r
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
         __syncthreads();
         const float* tile = smem + stage * TNF * TW;
         const int nvalid = min(TNF, q.MS - t * TNF);
-        if (t == t0) {
+        if (!FAST && t == t0) {
             // reference point of the lazy soft-max: the logit of the first streamed row of this split
             const float2* b = reinterpret_cast<const float2*>(tile + fs * slice_floats(DP, F));
 #pragma unroll
@@ -289,6 +295,12 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
                 }
                 const float D0 = slice_sum<F>(a0.x + a0.y);
                 const float D1s = slice_sum<F>(a1.x + a1.y);
+                if constexpr (FAST) {
+                    const float e0 = ex2_approx(D0 * -q.coef);
+                    const float e1 = has1 ? ex2_approx(D1s * -q.coef) : 0.f;
+                    s[r] += e0 + e1;
+                    continue;
+                }
                 const float D1 = has1 ? D1s : INFINITY;
                 float x0 = fmaf(D0, -q.coef, -m[r]);
                 float x1 = fmaf(D1, -q.coef, -m[r]);
@@ -473,7 +485,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
 template <int P, int DP, int F>
 int launch_fwd_pd(const FwdParams& q, dim3 grid, cudaStream_t st) {
     constexpr int R = fwd_rows_per_thread(DP);
-    auto kern = lpnce_fwd_kernel<P, DP, R, kCW, F>;
+    auto kern = q.fast ? lpnce_fwd_kernel<P, DP, R, kCW, F, true> : lpnce_fwd_kernel<P, DP, R, kCW, F, false>;
     const size_t smem = fwd_smem_bytes(DP, R, F);
     if (smem > 48 * 1024)
         CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -500,7 +512,7 @@ int occ_fwd_pd() {
     if (cached == 0) {
         constexpr int R = fwd_rows_per_thread(DP);
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_fwd_kernel<P, DP, R, kCW, F>, kThreads, fwd_smem_bytes(DP, R, F)) != cudaSuccess) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_fwd_kernel<P, DP, R, kCW, F, false>, kThreads, fwd_smem_bytes(DP, R, F)) != cudaSuccess) n = 1;
         cached = n < 1 ? 1 : n;
     }
     return cached;

@@ -59,3 +59,72 @@ def test_graphed_step_with_fused_mixing(cuda_device, monkeypatch):
         a = fused(z1, z2).clone()
         b = plain(z1, z2).clone()
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (a, b)
+
+
+# ---- fast forward of the fused loss (CLICA_LPNCE_FAST=1: fixed reference point, underflow fallback in finalize) ----
+def _loss_run(z1, z2, z3, p, tau, compat, dev, roll):
+    from clica_b200 import functional as F
+    a = torch.tensor(z1, device=dev, requires_grad=True)
+    b = torch.tensor(z2, device=dev, requires_grad=True)
+    n = torch.roll(a, 1, 0) if roll else torch.tensor(z3, device=dev, requires_grad=True)
+    mean, per_item, pos_mean, neg_mean = F.lp_infonce(a, b, n, p, tau, 0.5, compat)
+    mean.backward()
+    return mean.item(), per_item.detach().cpu().numpy(), a.grad.cpu().numpy(), b.grad.cpu().numpy()
+
+
+def test_fast_forward_on_the_golden_vectors(cuda_device, monkeypatch):
+    import numpy as np
+    from conftest import golden_loss_cases, load_golden
+    monkeypatch.setenv("CLICA_LPNCE_FAST", "1")
+    for name in golden_loss_cases():
+        g = load_golden("lpnce_" + name)
+        if not bool(g["pow"]) or "gl" in g or name.endswith("_cpupin"):
+            continue
+        roll = bool(g["roll"])
+        mean, li, g1, g2 = _loss_run(g["z1"], g["z2"], None if roll else g["z3"], float(g["p"]), float(g["tau"]),
+                                     bool(g["compat"]), cuda_device, roll) if float(g["alpha"]) == 0.5 else (None,) * 4
+        if mean is None:
+            continue
+        scale = max(1.0, float(np.abs(g["loss_i_64"]).max()))
+        assert np.abs(li - g["loss_i_64"]).max() <= 5e-6 * scale, name      # includes the underflowing rows (fallback)
+        gmax = max(float(np.abs(g["g1_64"]).max()), 1e-30)
+        tol = 2e-5 if float(g["p"]) in (1.0, 2.0, 3.0, 4.0) else 3e-5
+        assert np.abs(g1 - g["g1_64"]).max() <= tol * gmax, name
+        assert np.abs(g2 - g["g2_64"]).max() <= tol * gmax, name
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 2.5])
+@pytest.mark.parametrize("B,M,d", [(300, 517, 10), (257, 1031, 40), (130, 257, 128), (6144, 6144, 10)])
+def test_fast_forward_matches_the_default_forward(p, B, M, d, cuda_device, monkeypatch):
+    import numpy as np
+    rng = np.random.RandomState(B + M + d)
+    z1 = rng.randn(B, d).astype(np.float32) * 0.7
+    z2 = (z1 + 0.05 * rng.randn(B, d)).astype(np.float32)
+    z3 = rng.randn(M, d).astype(np.float32) * 0.7
+    monkeypatch.setenv("CLICA_LPNCE_FAST", "0")
+    ref = _loss_run(z1, z2, z3, float(p), 0.6, True, cuda_device, False)
+    monkeypatch.setenv("CLICA_LPNCE_FAST", "1")
+    out = _loss_run(z1, z2, z3, float(p), 0.6, True, cuda_device, False)
+    scale = max(1.0, float(np.abs(ref[1]).max()))
+    assert abs(out[0] - ref[0]) <= 2e-6 * scale
+    assert np.abs(out[1] - ref[1]).max() <= 2e-6 * scale
+    gmax = float(np.abs(ref[2]).max())
+    assert np.abs(out[2] - ref[2]).max() <= 1e-5 * gmax and np.abs(out[3] - ref[3]).max() <= 1e-5 * gmax
+
+
+def test_fast_forward_underflow_fallback(cuda_device, monkeypatch):
+    """Every logit of every row far below 2^-126 without the positive pair in the denominator (non-compat mode): the
+    fast kernel's sums flush to zero and the finalize kernel must recompute the rows; compare with the fp64 oracle."""
+    import numpy as np
+    from oracle import c_oracle
+    rng = np.random.RandomState(11)
+    z1 = rng.randn(70, 6).astype(np.float32)
+    z2 = (z1 + 0.05 * rng.randn(70, 6)).astype(np.float32)
+    z3 = (rng.randn(90, 6) * 2 + 9).astype(np.float32)
+    monkeypatch.setenv("CLICA_LPNCE_FAST", "1")
+    mean, li, g1, g2 = _loss_run(z1, z2, z3, 2.0, 0.05, False, cuda_device, False)
+    ref = c_oracle.lpnce(z1, z2, z3, 2, 0.05, 0.5, include_pos=False)
+    scale = max(1.0, float(np.abs(ref["loss_i"]).max()))
+    assert np.isfinite(li).all()
+    assert np.abs(li - ref["loss_i"]).max() <= 5e-6 * scale
+    assert np.abs(g1 - ref["g1"]).max() <= 2e-5 * max(float(np.abs(ref["g1"]).max()), 1e-30)
