@@ -64,6 +64,7 @@ class GraphedTrainStep:
         self.stream = torch.cuda.Stream(dev)
         self.launches_per_replay = 0
         self.steps_taken = 0
+        self._replayed = torch.cuda.Event()      # recorded after every replay (guards the pinned staging buffer)
         self._capture(max(int(warmup), 1))
 
     # the recorded body -------------------------------------------------------------------------------------
@@ -140,6 +141,7 @@ class GraphedTrainStep:
         if not z1.is_cuda:
             if not self.host_io:
                 raise RuntimeError("GraphedTrainStep(host_io=False) takes device tensors")
+            self._replayed.synchronize()         # the previous replay's H2D copy has finished reading the buffer
             self.z_host[:B].copy_(z1)
             self.z_host[B:].copy_(z2)
         else:
@@ -152,6 +154,7 @@ class GraphedTrainStep:
         """One training step on the staged inputs (asynchronous). Returns the device tensor
         ``[loss, pos_mean, neg_mean]`` that the step overwrites."""
         self.graph.replay()
+        self._replayed.record(torch.cuda.current_stream(self.device))
         self.steps_taken += 1
         torch.autograd.graph.increment_version(self.params)     # the graph updated the parameters in place
         return self.out_dev
