@@ -318,14 +318,23 @@ def run_ours(args):
             watchdog = threading.Timer(150.0, _wedged)
             watchdog.daemon = True
             watchdog.start()
-        graphed = GraphedTrainStep(f, g, crit, B_local, n, lr=1e-4, host_io=False,
-                                   group=(dist.group.WORLD if world > 1 else None))
-        graphed.stage(z1_d, z2_d)
-        graphed.replay()
-        torch.cuda.synchronize()
+        try:
+            graphed = GraphedTrainStep(f, g, crit, B_local, n, lr=1e-4, host_io=False,
+                                       group=(dist.group.WORLD if world > 1 else None))
+            graphed.stage(z1_d, z2_d)
+            graphed.replay()
+            torch.cuda.synchronize()
+            step_mode = "cuda_graph"
+        except Exception as exc:           # same kernels either way: time the eager step and say so in the JSON line
+            if world > 1:
+                raise                      # ranks must not diverge on the step flavour
+            sys.stderr.write(f"bench.py: CUDA-graph step unavailable ({exc!r}); timing the eager step\n")
+            graphed = None
+            args.graph = False
+            step_mode = "eager (graph capture failed: " + repr(exc)[:120] + ")"
+            torch.cuda.synchronize()
         if watchdog is not None:
             watchdog.cancel()
-        step_mode = "cuda_graph"
 
     def step_device():
         if graphed is not None:
