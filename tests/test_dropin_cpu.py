@@ -83,3 +83,27 @@ def test_cuda_path_fails_loudly_without_a_gpu():
         F.lp_infonce(a, a, a, 2.0)
     with pytest.raises(RuntimeError):
         F.mlp_forward(a, [torch.randn(5, 3)], [torch.randn(5)])
+
+
+def test_graphed_step_refuses_a_cpu_model():
+    """GraphedTrainStep is CUDA-only: a CPU encoder must raise, not run some other path."""
+    import pytest
+    import torch
+    from clica_b200.graphed import GraphedTrainStep
+    f = torch.nn.Sequential(torch.nn.Linear(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedTrainStep(f, None, object(), 8, 4)
+
+
+def test_mixing_plan_recognises_only_the_frozen_bias_free_stack():
+    import torch
+    from clica_b200 import functional as F
+    from clica_b200 import synth
+    g = synth.build_mixing(6, 3)
+    ws, slope = F.mixing_plan(g)
+    assert len(ws) == 3 and slope == 0.2
+    assert F.mixing_plan(torch.nn.Sequential(torch.nn.Linear(6, 6))) is None                  # has a bias
+    g2 = synth.build_mixing(6, 2)
+    g2[0].weight.requires_grad = True
+    assert F.mixing_plan(g2) is None                                                          # trainable
+    assert F.mixing_plan(torch.nn.Sequential(*list(g)[:2])) is None                           # ends on an activation
