@@ -239,14 +239,14 @@ SplitPlan plan_splits(int rows, int rows_cta, int MS, int tile_cols, int sm_coun
     return pl;
 }
 // resident CTAs per SM of the kernel that will run (cudaOccupancy..., cached per instantiation)
-int occ_fwd(int pc, Shape sh) {
+int occ_fwd(int pc, Shape sh, int fast) {
     int n;
     switch (pc) {
-        case 1: n = occ_fwd_p1(sh.DP, sh.F); break;
-        case 2: n = occ_fwd_p2(sh.DP, sh.F); break;
-        case 3: n = occ_fwd_p3(sh.DP, sh.F); break;
-        case 4: n = occ_fwd_p4(sh.DP, sh.F); break;
-        default: n = occ_fwd_p0(sh.DP, sh.F); break;
+        case 1: n = occ_fwd_p1(sh.DP, sh.F, fast); break;
+        case 2: n = occ_fwd_p2(sh.DP, sh.F, fast); break;
+        case 3: n = occ_fwd_p3(sh.DP, sh.F, fast); break;
+        case 4: n = occ_fwd_p4(sh.DP, sh.F, fast); break;
+        default: n = occ_fwd_p0(sh.DP, sh.F, fast); break;
     }
     return n < 1 ? 1 : n;
 }
@@ -263,9 +263,13 @@ int occ_bwd(int pc, Shape sh) {
 }
 // The split plan only depends on (rows, MS, DP, #SMs) -- NOT on the exponent -- so that the workspace queries
 // (which do not know p) and the launches agree: the most common occupancy of the family is used (p = 2).
+// (the experimental fast forward -- CLICA_LPNCE_FAST, read here so that the workspace query and the launch agree --
+// owns more rows per thread at small d and has its own occupancy)
+int fwd_fast_enabled() { return env_flag("CLICA_LPNCE_FAST", 0) != 0; }
 SplitPlan plan_fwd(int B, int M, Shape sh, int sms) {
-    const int R = fwd_rows_per_thread(sh.DP);
-    return plan_splits(B, rows_per_cta(R, sh.F), M, tile_rows(sh.F), sms, occ_fwd(2, sh));
+    const int fast = fwd_fast_enabled();
+    const int R = fwd_rows_per_thread(sh.DP, fast != 0);
+    return plan_splits(B, rows_per_cta(R, sh.F), M, tile_rows(sh.F), sms, occ_fwd(2, sh, fast));
 }
 SplitPlan plan_bwd(int rows, int MS, Shape sh, int sms) {
     const int R = bwd_rows_per_thread(sh.DP);
@@ -369,7 +373,7 @@ extern "C" int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld
     q.coef = kLog2e / tau; q.pg = p;
     q.tiles_per_split = pl.tiles_per_split; q.flat16 = is_flat16(z3, ld3, d, sh);
     q.part_m = w.part_m; q.part_s = w.part_s; q.part_stride = B; q.counter = w.counter;
-    q.fast = env_flag("CLICA_LPNCE_FAST", 0) != 0;        // EXPERIMENTAL, off by default
+    q.fast = fwd_fast_enabled();                           // EXPERIMENTAL, off by default
     { LaunchScope ls(st, kFamLossFwd); rc = dispatch_fwd(p_code(p), sh, q, dim3(pl.row_tiles, pl.nsplit, 1), st); }
     if (rc) return rc;
 

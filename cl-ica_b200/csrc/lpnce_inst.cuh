@@ -12,8 +12,8 @@ int CLICA_CAT(launch_fwd_p, CLICA_P)(int DP, int F, const FwdParams& q, dim3 g, 
 int CLICA_CAT(launch_bwd_p, CLICA_P)(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s) {
     CLICA_DISPATCH_DPF(CLICA_P, DP, F, launch_bwd_pd, q, g, s)
 }
-int CLICA_CAT(occ_fwd_p, CLICA_P)(int DP, int F) {
-    CLICA_DISPATCH_DPF(CLICA_P, DP, F, occ_fwd_pd)
+int CLICA_CAT(occ_fwd_p, CLICA_P)(int DP, int F, int fast) {
+    CLICA_DISPATCH_DPF(CLICA_P, DP, F, occ_fwd_pd, fast)
 }
 int CLICA_CAT(occ_bwd_p, CLICA_P)(int DP, int F) {
     CLICA_DISPATCH_DPF(CLICA_P, DP, F, occ_bwd_pd)

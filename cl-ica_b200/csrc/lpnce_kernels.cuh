@@ -32,7 +32,9 @@ constexpr int kCW = 4;            // warps of a CTA that split the streamed rows
 constexpr float kRescale = 24.f;  // lazy soft-max re-scaling threshold (log2 units)
 
 // rows owned per thread: 2 while the register budget allows it
-constexpr int fwd_rows_per_thread(int DP) { return DP <= 12 ? 2 : 1; }
+// (the EXPERIMENTAL fast forward owns 4 rows per thread for d <= 10: its inner loop has no per-pair soft-max
+// bookkeeping left to hide the broadcast LDS and the loop control behind)
+constexpr int fwd_rows_per_thread(int DP, bool fast = false) { return (fast && DP <= 5) ? 4 : (DP <= 12 ? 2 : 1); }
 constexpr int bwd_rows_per_thread(int DP) { return DP <= 5 ? 2 : 1; }
 constexpr int rows_per_cta(int R, int F = 1) { return (32 / F) * R * (kWarps / kCW); }
 // shared-memory layout of a streamed row: F feature slices of 2*DP floats (+4 floats of padding when F > 1 so
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
                 const float D1s = slice_sum<F>(a1.x + a1.y);
                 if constexpr (FAST) {
                     const float e0 = ex2_approx(D0 * -q.coef);
-                    const float e1 = has1 ? ex2_approx(D1s * -q.coef) : 0.f;
+                    const float e1 = ex2_approx(has1 ? D1s * -q.coef : -INFINITY);   // ex2(-inf) = +0, branch-free
                     s[r] += e0 + e1;
                     continue;
                 }
@@ -484,9 +486,9 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
 // ---- launch helpers (instantiated once per exponent, see lpnce_inst.cuh) ---------------------------
 template <int P, int DP, int F>
 int launch_fwd_pd(const FwdParams& q, dim3 grid, cudaStream_t st) {
-    constexpr int R = fwd_rows_per_thread(DP);
-    auto kern = q.fast ? lpnce_fwd_kernel<P, DP, R, kCW, F, true> : lpnce_fwd_kernel<P, DP, R, kCW, F, false>;
-    const size_t smem = fwd_smem_bytes(DP, R, F);
+    constexpr int R = fwd_rows_per_thread(DP), RF = fwd_rows_per_thread(DP, true);
+    auto kern = q.fast ? lpnce_fwd_kernel<P, DP, RF, kCW, F, true> : lpnce_fwd_kernel<P, DP, R, kCW, F, false>;
+    const size_t smem = q.fast ? fwd_smem_bytes(DP, RF, F) : fwd_smem_bytes(DP, R, F);
     if (smem > 48 * 1024)
         CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(q);
@@ -507,15 +509,19 @@ int launch_bwd_pd(const BwdParams& q, dim3 grid, cudaStream_t st) {
 
 // resident CTAs per SM of one instantiation (sizes the grid: splits are chosen so that the CTAs fill whole waves)
 template <int P, int DP, int F>
-int occ_fwd_pd() {
-    static int cached = 0;
-    if (cached == 0) {
-        constexpr int R = fwd_rows_per_thread(DP);
+int occ_fwd_pd(int fast) {
+    static int cached[2] = {0, 0};
+    const int i = fast ? 1 : 0;
+    if (cached[i] == 0) {
+        constexpr int R = fwd_rows_per_thread(DP), RF = fwd_rows_per_thread(DP, true);
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_fwd_kernel<P, DP, R, kCW, F, false>, kThreads, fwd_smem_bytes(DP, R, F)) != cudaSuccess) n = 1;
-        cached = n < 1 ? 1 : n;
+        cudaError_t e = fast
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_fwd_kernel<P, DP, RF, kCW, F, true>, kThreads, fwd_smem_bytes(DP, RF, F))
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lpnce_fwd_kernel<P, DP, R, kCW, F, false>, kThreads, fwd_smem_bytes(DP, R, F));
+        if (e != cudaSuccess) n = 1;
+        cached[i] = n < 1 ? 1 : n;
     }
-    return cached;
+    return cached[i];
 }
 template <int P, int DP, int F>
 int occ_bwd_pd() {
@@ -562,7 +568,7 @@ int launch_bwd_p1(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p2(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p3(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p4(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
-int occ_fwd_p0(int DP, int F); int occ_fwd_p1(int DP, int F); int occ_fwd_p2(int DP, int F); int occ_fwd_p3(int DP, int F); int occ_fwd_p4(int DP, int F);
+int occ_fwd_p0(int DP, int F, int fast); int occ_fwd_p1(int DP, int F, int fast); int occ_fwd_p2(int DP, int F, int fast); int occ_fwd_p3(int DP, int F, int fast); int occ_fwd_p4(int DP, int F, int fast);
 int occ_bwd_p0(int DP, int F); int occ_bwd_p1(int DP, int F); int occ_bwd_p2(int DP, int F); int occ_bwd_p3(int DP, int F); int occ_bwd_p4(int DP, int F);
 
 }  // namespace clica
