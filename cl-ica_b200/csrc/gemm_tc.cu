@@ -561,6 +561,29 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     }
 }
 
+constexpr int kSplitMaxJobs = 8;
+struct SplitMultiArgs {
+    SplitJob job[kSplitMaxJobs];
+    int block_start[kSplitMaxJobs + 1];     // prefix sums of ceil(rows * ld_dst / 256)
+    int n;
+};
+__global__ void __launch_bounds__(256) split_planes_multi_kernel(const SplitMultiArgs a) {
+    int t = 0;
+    while (t + 1 < a.n && a.block_start[t + 1] <= (int)blockIdx.x) ++t;
+    const SplitJob& j = a.job[t];
+    const long long idx = (long long)((int)blockIdx.x - a.block_start[t]) * 256 + threadIdx.x;
+    if (idx >= (long long)j.rows * j.ld_dst) return;
+    const int r = (int)(idx / j.ld_dst), c = (int)(idx - (long long)r * j.ld_dst);
+    const float v = (c < j.cols) ? __ldg(j.src + (size_t)r * j.ld_src + c) : 0.f;
+    if (j.lo != nullptr) {
+        const float h = round_to_tf32(v);
+        j.hi[idx] = h;
+        j.lo[idx] = round_to_tf32(v - h);
+    } else {
+        j.hi[idx] = v;
+    }
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -678,6 +701,24 @@ int tc_split_planes(const float* src, int ld_src, int rows, int cols, float* hi,
     const long long n = (long long)rows * ld_dst;
     { LaunchScope ls(st, kFamMisc); split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ld_src, rows, cols, hi, lo, ld_dst); }
     CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tc_split_planes_multi(const SplitJob* jobs, int n, cudaStream_t st) {
+    for (int first = 0; first < n; first += kSplitMaxJobs) {
+        SplitMultiArgs a;
+        a.n = (n - first < kSplitMaxJobs) ? (n - first) : kSplitMaxJobs;
+        int blocks = 0;
+        for (int t = 0; t < a.n; ++t) {
+            a.job[t] = jobs[first + t];
+            a.block_start[t] = blocks;
+            blocks += (int)(((long long)a.job[t].rows * a.job[t].ld_dst + 255) / 256);
+        }
+        a.block_start[a.n] = blocks;
+        if (blocks == 0) continue;
+        { LaunchScope ls(st, kFamMisc); split_planes_multi_kernel<<<blocks, 256, 0, st>>>(a); }
+        CLICA_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 

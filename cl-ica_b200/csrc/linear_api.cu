@@ -241,6 +241,16 @@ PlanesIn weight_planes(const MlpPlan& p, const MlpWs& w, int l) {
     return a;
 }
 int pack_weights(const MlpPlan& p, const MlpWs& w, const float* const* W, cudaStream_t st) {
+    if (env_flag("CLICA_PACK_FUSED", 0) != 0) {      // EXPERIMENTAL: all eligible layers in one launch
+        SplitJob jobs[64];
+        int n = 0;
+        for (int l = 0; l < p.L && l < 64; ++l) {
+            if (!p.layer_eligible(l)) continue;
+            PlanesIn wp = weight_planes(p, w, l);
+            jobs[n++] = SplitJob{W[l], p.w[l], p.w[l + 1], p.w[l], (float*)wp.hi, (float*)wp.lo, wp.ld};
+        }
+        return tc_split_planes_multi(jobs, n, st);
+    }
     for (int l = 0; l < p.L; ++l) {
         if (!p.layer_eligible(l)) continue;
         PlanesIn wp = weight_planes(p, w, l);

@@ -128,3 +128,23 @@ def test_fast_forward_underflow_fallback(cuda_device, monkeypatch):
     assert np.isfinite(li).all()
     assert np.abs(li - ref["loss_i"]).max() <= 5e-6 * scale
     assert np.abs(g1 - ref["g1"]).max() <= 2e-5 * max(float(np.abs(ref["g1"]).max()), 1e-30)
+
+
+def test_fused_weight_packing_is_bit_identical(cuda_device, monkeypatch):
+    """CLICA_PACK_FUSED=1 packs the five hidden weight matrices in one launch: same arithmetic, same planes."""
+    from clica_b200 import functional as F
+    n, M = 10, 777
+    widths = [n, 10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n, n]
+    g = torch.Generator().manual_seed(5)
+    Ws = [((torch.rand(widths[i + 1], widths[i], generator=g) * 2 - 1) / widths[i] ** 0.5).to(cuda_device) for i in range(7)]
+    bs = [((torch.rand(widths[i + 1], generator=g) * 2 - 1) / widths[i] ** 0.5).to(cuda_device) for i in range(7)]
+    x = torch.randn(M, n, generator=g).to(cuda_device)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CLICA_PACK_FUSED", flag)
+        F.invalidate_packed_weights()
+        launches0 = F._lib.load().clica_launch_count(6)
+        outs.append(F.mlp_forward(x, Ws, bs, slope=0.01, mode=0).clone())
+        outs.append(F._lib.load().clica_launch_count(6) - launches0)
+    assert torch.equal(outs[0], outs[2])
+    assert outs[1] == 5 and outs[3] == 1          # five split launches -> one
