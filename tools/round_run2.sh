@@ -14,7 +14,7 @@ import json; d=json.load(open('$O/bench_pair2_${TAG}.json')); print('PAIR=2 ms/s
 timeout -k 10 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench_stdout_${TAG}.log 2>&1
 echo "ncu list rc=$?"
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|lpnce|skinny|gemm_simt|adam|split_planes|colsum' -s 120 -c 48 -f -o $O/prof_${TAG}_step \
+timeout -k 10 420 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|lpnce|skinny|gemm_simt|adam|split_planes|colsum' -s 120 -c 30 -f -o $O/prof_${TAG}_step \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_full_stdout_${TAG}.log 2>&1
 echo "ncu full rc=$?"
 timeout -k 10 150 python bench.py --steps 10 --warmup 3 --workload c3 --scaling strong --no-cpu-baseline 2>$O/bench_${TAG}_c3.err | tail -1 > $O/bench_${TAG}_c3.json
