@@ -21,7 +21,7 @@ from ._lib import ClicaError, build  # noqa: E402,F401
 
 def __getattr__(name):
     # functional / optim / sharded import torch; keep `import clica_b200` itself light
-    if name in ("functional", "optim", "sharded", "launch", "graphed"):
+    if name in ("functional", "optim", "sharded", "launch", "graphed", "vendor", "samplers", "synth"):
         import importlib
         return importlib.import_module("clica_b200." + name)
     raise AttributeError(name)

@@ -50,7 +50,10 @@ SIGNATURES = {
     "clica_mlp_fwd": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _c_int, _c_float, _c_int, _vp, _vp, _c_size_t, _vp]),
     "clica_mlp_bwd": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_float, _c_int, _vp, _c_int,
                                _vp, _c_size_t, _vp]),
+    "clica_mlp_bwd_range": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_float, _c_int, _vp, _c_int,
+                                     _c_int, _c_int, _vp, _c_size_t, _vp]),
     "clica_mixing_fwd": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_float, _vp, _c_int, _vp]),
+    "clica_tc_set_sm_reserve": (_c_int, [_c_int]),
     "clica_launch_count": (ctypes.c_longlong, [_c_int]),
     "clica_prof_enable": (_c_int, [_c_int]),
     "clica_prof_collect": (_c_int, [_vp, _vp]),

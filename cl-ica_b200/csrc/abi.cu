@@ -39,6 +39,9 @@ int get_device_info(DeviceInfo* out) {
     return 0;
 }
 
+namespace { std::atomic<int> g_sm_reserve{0}; }
+int tc_sm_reserve() { return g_sm_reserve.load(std::memory_order_relaxed); }
+
 // ---- launch accounting ---------------------------------------------------------------------------------
 namespace {
 constexpr int kProfSlots = 8192;
@@ -117,6 +120,12 @@ extern "C" int clica_prof_collect(float* ms_by_family, int* scopes_by_family) {
     }
     ps.next.store(0);
     return 0;
+}
+
+extern "C" int clica_tc_set_sm_reserve(int sms) {
+    CLICA_REQUIRE(sms >= 0 && sms <= 64, CLICA_E_BADARG, "tc_set_sm_reserve: %d outside [0, 64]", sms);
+    const int prev = clica::g_sm_reserve.exchange(sms);
+    return prev < 0 ? 0 : 0;
 }
 
 extern "C" int clica_abi_version(void) { return CLICA_ABI_VERSION; }

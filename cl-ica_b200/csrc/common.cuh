@@ -40,6 +40,7 @@ struct DeviceInfo {
     int ok = 0;
 };
 int get_device_info(DeviceInfo* out);   // cached per device; defined in abi.cu
+int tc_sm_reserve();                    // SMs the persistent tcgen05 GEMMs leave free (clica_tc_set_sm_reserve); abi.cu
 
 // ---- launch accounting / optional per-family CUDA-event timing (bench.py's roofline numbers) ------
 enum KernelFamily : int {
@@ -60,6 +61,18 @@ struct LaunchScope {
     cudaStream_t st_;
     int slot_;
 };
+
+// true the first time it is called for (`flags`, current device): per-function attributes such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize are per device, so "set once per process" is not enough.
+// Callers set the attributes when it returns true (idempotent, so a rare double set under a race is harmless).
+struct PerDeviceOnce { bool done[64] = {}; };
+inline bool first_on_this_device(PerDeviceOnce& o) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (o.done[dev]) return false;
+    o.done[dev] = true;
+    return true;
+}
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // integer environment switch, read at every call (cheap; lets tests toggle experimental paths in-process)

@@ -723,6 +723,9 @@ int tc_split_planes_multi(const SplitJob* jobs, int n, cudaStream_t st) {
 }
 
 int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
+    // SMs left free for a concurrent kernel (the NCCL all-reduce of the previous gradient bucket in the multi-GPU
+    // step): a persistent grid that does not fit entirely would serialise its last CTAs behind the first ones
+    { const int r = tc_sm_reserve(); if (r > 0 && sm_count - r >= 8) sm_count -= r; }
     CLICA_REQUIRE(g.Mo >= 1 && g.No >= 1 && g.Kr >= 1, CLICA_E_BADARG, "tc_gemm: empty problem");
     CLICA_REQUIRE(g.A.hi && g.B.hi, CLICA_E_BADARG, "tc_gemm: null operand");
     CLICA_REQUIRE((g.A.lo != nullptr) == (g.B.lo != nullptr), CLICA_E_BADARG, "tc_gemm: operands must both be split or both plain");
@@ -790,16 +793,17 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     splits = ceil_div(q.kb_total, q.kb_per_split);
     q.splits = splits;
     const size_t smem = (size_t)q.stages * stage_bytes + smem_fixed;
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int max_dyn = (int)smem_cap;
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-        attr_set = true;
+    {   // the opt-in is per device (context)
+        static PerDeviceOnce attr;
+        if (first_on_this_device(attr)) {
+            const int max_dyn = (int)smem_cap;
+            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        }
     }
     const int total = tiles * splits;
     const int units = sm_count / ctas;

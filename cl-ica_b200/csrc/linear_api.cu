@@ -50,11 +50,10 @@ int launch_skinny_kin(const SkinnyKinParams& q, cudaStream_t st) {
 }
 int launch_skinny_nout_small(const SkinnyNoutParams& q, cudaStream_t st) {
     const size_t smem = nout_small_smem_bytes(q.N);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (first_on_this_device(attr)) {
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)nout_small_smem_bytes(kNsMaxN)));
-        attr = true;
     }
     LaunchScope ls(st, kFamGemmSimt);
     skinny_nout_small_kernel<<<ceil_div(q.M, kNsRows), 256, smem, st>>>(q);
@@ -66,11 +65,10 @@ int launch_skinny_nout(const SkinnyNoutParams& q, int sm_count, cudaStream_t st)
     const size_t smem = (size_t)q.N * q.K * sizeof(float);
     int grid = ceil_div(q.M, 8);
     if (grid > 8 * sm_count) grid = 8 * sm_count;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (first_on_this_device(attr)) {
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
     }
     LaunchScope ls(st, kFamGemmSimt);
     if (q.N <= 16) skinny_nout_kernel<16><<<grid, 256, smem, st>>>(q);
@@ -81,11 +79,10 @@ int launch_skinny_nout(const SkinnyNoutParams& q, int sm_count, cudaStream_t st)
 bool skinny_dw_ok(int N, int K) { return (size_t)kSkRows * (N + K + 1) * sizeof(float) <= 64 * 1024 && (size_t)N * (K + 1) <= 32768; }
 int launch_skinny_dw(const SkinnyDwParams& q, int sm_count, cudaStream_t st) {
     const size_t smem = (size_t)kSkRows * (q.N + q.K + 1) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (first_on_this_device(attr)) {
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_dw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
     }
     LaunchScope ls(st, kFamGemmSimt);
     const int tiles = ceil_div(q.M, kSkRows);
@@ -393,9 +390,23 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
                              const float* g_out, float* const* dW, float* const* db, float* g_in,
                              int M, float slope, int mode, const void* packed_weights, int grads_prezeroed,
                              void* ws, size_t ws_bytes, void* stream) {
+    return clica_mlp_bwd_range(L, widths, W, acts, g_out, dW, db, g_in, M, slope, mode, packed_weights,
+                               grads_prezeroed, L - 1, 0, ws, ws_bytes, stream);
+}
+
+// Layers l_first, l_first - 1, ..., l_last of the backward chain.  The gradient w.r.t. the pre-activation of layer
+// l_first comes from g_out (l_first == L - 1) or from the workspace, where the previous range call left it: a whole
+// backward may be issued as consecutive ranges with the SAME workspace on the SAME stream (the multi-GPU step does so
+// to start the all-reduce of a finished layer's gradients while the earlier layers are still being differentiated).
+extern "C" int clica_mlp_bwd_range(int L, const int* widths, const float* const* W, const float* const* acts,
+                                   const float* g_out, float* const* dW, float* const* db, float* g_in,
+                                   int M, float slope, int mode, const void* packed_weights, int grads_prezeroed,
+                                   int l_first, int l_last, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_mode(mode);
     if (rc) return rc;
     CLICA_REQUIRE(L >= 1 && L <= 64 && widths && W && acts && g_out && dW && db && M >= 1, CLICA_E_BADARG, "mlp_bwd: bad arguments");
+    CLICA_REQUIRE(l_first <= L - 1 && l_last >= 0 && l_last <= l_first, CLICA_E_BADARG,
+                  "mlp_bwd_range: layers [%d .. %d] outside [%d .. 0]", l_first, l_last, L - 1);
     DeviceInfo di;
     if ((rc = get_device_info(&di))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -408,7 +419,13 @@ extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, co
 
     PlanesIn g = {g_out, nullptr, widths[L]};     // dL/d(pre-activation of layer l), starts as dL/d(output)
     bool db_done = false;                         // db[l] already accumulated by the epilogue that produced g
-    for (int l = L - 1; l >= 0; --l) {
+    if (l_first < L - 1) {                        // continue where the previous range stopped
+        g.ld = p.act_ld(l_first + 1);
+        g.hi = w.gbuf[(l_first + 1) & 1];
+        g.lo = (p.nplanes == 2) ? g.hi + (size_t)M * g.ld : nullptr;
+        db_done = true;
+    }
+    for (int l = l_first; l >= l_last; --l) {
         const int K = widths[l], N = widths[l + 1];
         PlanesIn x = act_in(p, acts, l);
         // dW[l] = g^T x ; db[l] = column sums of g

@@ -120,9 +120,10 @@ struct Lp {
         if constexpr (P == 2) {
             return __ffma2_rn(make_float2(w, w), t, g);
         } else if constexpr (P == 1) {
-            // sign(0) = 0: a zero difference contributes exactly nothing (torch masks it too)
-            g.x += (t.x == 0.f) ? 0.f : copysignf(w, t.x);
-            g.y += (t.y == 0.f) ? 0.f : copysignf(w, t.y);
+            // w * sign(t), sign(0) = 0: a zero difference contributes exactly nothing (torch masks it too).  w keeps
+            // its own sign (negative upstream gradients, alpha > 1): copysignf(w, t) would drop it.
+            g.x += (t.x > 0.f) ? w : ((t.x < 0.f) ? -w : 0.f);
+            g.y += (t.y > 0.f) ? w : ((t.y < 0.f) ? -w : 0.f);
             return g;
         } else if constexpr (P == 3) {
             g.x = fmaf(w, t.x * fabsf(t.x), g.x);

@@ -1,7 +1,8 @@
 """Locate the reference checkout (for re-exporting everything that is NOT on the hot path).
 
 Search order: $CLICA_REFERENCE_DIR, then every sys.path entry that holds a ``losses.py`` and an
-``encoders.py`` which are not ours.  Returns None when no reference is reachable (e.g. on the GPU box)."""
+``encoders.py`` which are not ours, then the repo's ``baseline/_ref`` (the read-only copy ``build()`` places there;
+git-ignored, it travels to the GPU box).  Returns None when no reference is reachable."""
 import importlib.util
 import os
 import sys
@@ -15,6 +16,7 @@ def reference_dir():
     if os.environ.get("CLICA_REFERENCE_DIR"):
         cands.append(os.environ["CLICA_REFERENCE_DIR"])
     cands += [p for p in sys.path if p]
+    cands.append(os.path.join(os.path.dirname(os.path.dirname(_HERE)), "baseline", "_ref"))
     for c in cands:
         c = os.path.abspath(c)
         if c == _HERE:

@@ -18,6 +18,37 @@ _vp = ctypes.c_void_p
 
 # ---- per-(device, stream) scratch ---------------------------------------------------------------------
 _workspaces = {}
+_retired = []          # outgrown workspaces, kept alive (see _workspace)
+
+# ---- gradient synchronisation hook of the encoder backward (multi-GPU) ----------------------------------
+_grad_sync = None
+GRAD_BUCKET_BYTES = 2 << 20
+
+
+class grad_sync:
+    """Context manager: while active, ``_MLP.backward`` issues the encoder backward bucket by bucket (layers from the
+    output side; a bucket closes once it holds >= ``GRAD_BUCKET_BYTES`` of gradients) and calls ``fn(flat_slice)``
+    on each finished bucket -- a contiguous fp32 slice holding that bucket's dW / db.  ``fn`` may return an object
+    with ``.wait()`` (e.g. ``dist.all_reduce(..., async_op=True)``): all of them are waited for (stream-wise) before
+    the backward returns, so the reduction of the last layers' gradients overlaps the GEMMs of the earlier ones."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.covered = set()       # id() of every parameter whose gradient went through `fn`
+
+    def __call__(self, flat_slice):
+        return self.fn(flat_slice)
+
+    def __enter__(self):
+        global _grad_sync
+        self.prev, _grad_sync = _grad_sync, self
+        return self
+
+    def __exit__(self, *exc):
+        global _grad_sync
+        _grad_sync = self.prev
+        return False
+
 
 
 def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
@@ -28,7 +59,12 @@ def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
     key = (device.index, stream, tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, device=device)
+        if buf is not None:
+            # a CUDA graph recorded on this stream may have baked the old pointer in (GraphedTrainStep); PyTorch hands
+            # out stream handles from a small pool, so an unrelated later user of the "same" stream must not free it
+            _retired.append(buf)
+        # zero-filled: the loss kernels keep self-resetting arrival counters at the head of their workspace
+        buf = torch.zeros(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
 
@@ -241,6 +277,7 @@ class _MLP(torch.autograd.Function):
             _lib.check(rc, "clica_mlp_fwd")
         ctx.save_for_backward(*acts[:-1], *Ws)
         ctx.cfg = (L, widths, float(slope), int(mode), [b is not None for b in bs])
+        ctx.param_ids = [id(t) for t in params]
         ctx.packed = packed
         return acts[-1]
 
@@ -254,23 +291,46 @@ class _MLP(torch.autograd.Function):
         dev = gy.device
         gy = gy.contiguous()
         with torch.cuda.device(dev):
-            # all parameter gradients live in ONE zero-initialised flat buffer (split-K / fused column sums accumulate)
-            sizes = [W.numel() for W in Ws] + [W.shape[0] for W in Ws]
-            offs, tot = [], 0
-            for n_el in sizes:
-                offs.append(tot)
-                tot += (n_el + 3) // 4 * 4                     # keep every tensor 16-byte aligned
+            # all parameter gradients live in ONE zero-initialised flat buffer (split-K / fused column sums accumulate),
+            # laid out in backward order [W_{L-1}, b_{L-1}, ..., W_0, b_0] so that the layers finished first form a
+            # contiguous prefix (gradient buckets of the multi-GPU step are plain slices)
+            offs_w, offs_b, tot = [0] * L, [0] * L, 0
+            for l in range(L - 1, -1, -1):
+                offs_w[l] = tot
+                tot += (Ws[l].numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned
+                offs_b[l] = tot
+                tot += (Ws[l].shape[0] + 3) // 4 * 4
             flat = torch.zeros(tot, dtype=torch.float32, device=dev)
-            dWs = [flat[offs[l]:offs[l] + sizes[l]].view_as(Ws[l]) for l in range(L)]
-            dbs = [flat[offs[L + l]:offs[L + l] + sizes[L + l]] for l in range(L)]
+            dWs = [flat[offs_w[l]:offs_w[l] + Ws[l].numel()].view_as(Ws[l]) for l in range(L)]
+            dbs = [flat[offs_b[l]:offs_b[l] + Ws[l].shape[0]] for l in range(L)]
             g_in = torch.empty_like(acts[0]) if ctx.needs_input_grad[0] else None
             cw = (ctypes.c_int * (L + 1))(*widths)
             nbytes = lib.clica_mlp_workspace_bytes(M, L, cw, mode)
             ws = _workspace(nbytes, dev, "mlp")
-            rc = lib.clica_mlp_bwd(L, cw, _ptr_array(Ws), _ptr_array(acts), gy.data_ptr(), _ptr_array(dWs),
-                                   _ptr_array(dbs), _ptr(g_in), M, slope, mode, ctx.packed[0], 1,
-                                   ws.data_ptr(), ws.numel(), _stream_ptr(dev))
-            _lib.check(rc, "clica_mlp_bwd")
+            # buckets: [(l_first, l_last, flat_begin, flat_end)]
+            if _grad_sync is None:
+                buckets = [(L - 1, 0, 0, tot)]
+            else:
+                buckets, l_first, begin = [], L - 1, 0
+                for l in range(L - 1, -1, -1):
+                    end = offs_b[l] + (Ws[l].shape[0] + 3) // 4 * 4
+                    if (end - begin) * 4 >= GRAD_BUCKET_BYTES or l == 0:
+                        buckets.append((l_first, l, begin, end))
+                        l_first, begin = l - 1, end
+            works = []
+            for (l_first, l_last, begin, end) in buckets:
+                rc = lib.clica_mlp_bwd_range(L, cw, _ptr_array(Ws), _ptr_array(acts), gy.data_ptr(), _ptr_array(dWs),
+                                             _ptr_array(dbs), _ptr(g_in), M, slope, mode, ctx.packed[0], 1,
+                                             l_first, l_last, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                _lib.check(rc, "clica_mlp_bwd_range")
+                if _grad_sync is not None:
+                    w = _grad_sync(flat[begin:end])
+                    if w is not None:
+                        works.append(w)
+            for w in works:
+                w.wait()
+            if _grad_sync is not None:
+                _grad_sync.covered.update(ctx.param_ids)
         grads = []
         for l in range(L):
             grads.append(dWs[l] if ctx.needs_input_grad[4 + 2 * l] else None)

@@ -51,6 +51,17 @@ class GraphedTrainStep:
         if group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(group)
+        if self.world > 1:
+            # the row-sharded loss only exists as CUDA kernels (no delegation to the reference's torch code): refuse
+            # what those kernels do not implement instead of silently training a different objective
+            for attr in ("p", "tau", "alpha", "simclr_compatibility_mode"):
+                if not hasattr(criterion, attr):
+                    raise TypeError("GraphedTrainStep(group=...): the criterion must be an LpSimCLRLoss "
+                                    f"(missing attribute {attr!r})")
+            if not getattr(criterion, "pow", True):
+                raise ValueError("GraphedTrainStep(group=...): LpSimCLRLoss(pow=False) is not implemented by the sharded CUDA loss")
+            if float(criterion.p) < 1.0:
+                raise ValueError("GraphedTrainStep(group=...): p < 1 is not implemented by the sharded CUDA loss")
         # EXPERIMENTAL (not yet run on a GPU, off by default): the frozen mixing net as one fused kernel
         self._mix = None
         if g is not None and os.environ.get("CLICA_FUSED_MIXING", "0") == "1":
@@ -85,8 +96,8 @@ class GraphedTrainStep:
             c = self.criterion
             total, _, parts = sharded.sharded_lp_infonce(a, b, float(c.p), float(c.tau), float(c.alpha),
                                                          bool(c.simclr_compatibility_mode), self.group)
-            total.backward()
-            sharded.allreduce_grads(self.params, self.group)
+            with sharded.overlapped_grad_allreduce(self.params, self.group):
+                total.backward()
         else:
             total, _, parts = self.criterion(None, None, None, a, b, torch.roll(a, 1, 0))
             total.backward()
@@ -100,6 +111,8 @@ class GraphedTrainStep:
         dev = self.device
         with torch.no_grad():
             saved = [p.detach().clone() for p in self.params]
+            # module buffers too (e.g. BatchNorm running statistics, which the warm-up batches would pollute)
+            saved_buffers = [(b, b.detach().clone()) for b in self.f.buffers()]
         cur = torch.cuda.current_stream(dev)
         self.stream.wait_stream(cur)
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
@@ -119,6 +132,8 @@ class GraphedTrainStep:
             with torch.no_grad():
                 for p, s in zip(self.params, saved):
                     p.copy_(s)
+                for b, s in saved_buffers:
+                    b.copy_(s)
                 for st in self.optimizer.state.values():
                     st["exp_avg"].zero_()
                     st["exp_avg_sq"].zero_()

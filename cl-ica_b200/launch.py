@@ -13,9 +13,19 @@ import sys
 import warnings
 
 
+def _default_reference():
+    if os.environ.get("CLICA_REFERENCE_DIR"):
+        return os.environ["CLICA_REFERENCE_DIR"]
+    if os.path.isfile("/root/reference/main_mlp.py"):
+        return "/root/reference"
+    from clica_b200 import vendor
+    return vendor.vendored_dir() or "/root/reference"
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--reference", default=os.environ.get("CLICA_REFERENCE_DIR", "/root/reference"))
+    ap.add_argument("--reference", default=_default_reference(),
+                    help="reference checkout (default: $CLICA_REFERENCE_DIR, /root/reference, then baseline/_ref)")
     ap.add_argument("--script", default="main_mlp.py")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     args = ap.parse_args(argv)

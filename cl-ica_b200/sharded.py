@@ -114,6 +114,14 @@ class _ShardedInfoNCE(torch.autograd.Function):
 def sharded_lp_infonce(a_local, b_local, p, tau=1.0, alpha=0.5, include_pos=True, group=None, ops=CudaOps):
     """Global-batch Lp-InfoNCE from local shards. Returns (global mean loss, local per-item loss,
     tensor([global pos_mean, global neg_mean])).  Equal shard sizes on every rank are required."""
+    if float(p) < 1.0:
+        raise ValueError("sharded_lp_infonce: p < 1 (losses.py:433-442) is not implemented by the sharded loss")
+    if float(tau) <= 0.0:
+        raise ValueError("sharded_lp_infonce: tau must be > 0")
+    if a_local.dim() != 2 or a_local.shape != b_local.shape:
+        raise ValueError(f"sharded_lp_infonce: expected two [B_local, d] tensors, got {tuple(a_local.shape)}, {tuple(b_local.shape)}")
+    if ops is CudaOps and a_local.shape[1] > 320:
+        raise ValueError(f"sharded_lp_infonce: feature width {a_local.shape[1]} > 320 is outside the CUDA kernels' domain")
     return _ShardedInfoNCE.apply(a_local, b_local, float(p), float(tau), float(alpha), bool(include_pos), group, ops)
 
 
@@ -134,8 +142,31 @@ def allreduce_grads(params: List[torch.nn.Parameter], group=None) -> None:
         off += n
 
 
+class overlapped_grad_allreduce:
+    """Context manager for ``loss.backward()``: the CUDA encoder's backward all-reduces (SUM) its parameter gradients
+    bucket by bucket as soon as each bucket is complete -- on NCCL's own stream, overlapping the remaining backward
+    GEMMs (``functional.grad_sync``).  On exit, gradients that did not pass through that hook (parameters outside the
+    fused Linear+LeakyReLU stack, or an encoder that ran on torch's own kernels) are reduced in one flattened bucket."""
+
+    def __init__(self, params, group=None):
+        from . import functional as F
+        self.params, self.group = list(params), group
+        self.sync = F.grad_sync(lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+
+    def __enter__(self):
+        self.sync.__enter__()
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        self.sync.__exit__(exc_type, exc, tb)
+        if exc_type is None:
+            rest = [p for p in self.params if id(p) not in self.sync.covered]
+            allreduce_grads(rest, self.group)
+        return False
+
+
 def sharded_train_step(f, g, optimizer, z1_local, z2_local, p, tau=1.0, alpha=0.5, group=None, ops=CudaOps,
-                       z12_local=None):
+                       z12_local=None, overlap=True):
     """The body of ``main_mlp.py:258-285`` (unsupervised branch) on one rank's shard of the global batch.
 
     Returns (global mean loss tensor, tensor([pos_mean, neg_mean])) -- 0-dim / 2-element device tensors; the
@@ -150,7 +181,11 @@ def sharded_train_step(f, g, optimizer, z1_local, z2_local, p, tau=1.0, alpha=0.
         a = f(g(z1_local))
         b = f(g(z2_local))
     loss, _, parts = sharded_lp_infonce(a, b, p, tau, alpha, True, group, ops)
-    loss.backward()
-    allreduce_grads([prm for prm in f.parameters()], group)
+    if overlap:
+        with overlapped_grad_allreduce(f.parameters(), group):     # the encoder backward reduces its own gradient buckets
+            loss.backward()
+    else:
+        loss.backward()
+        allreduce_grads([prm for prm in f.parameters()], group)
     optimizer.step()
     return loss.detach(), parts

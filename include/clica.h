@@ -188,6 +188,16 @@ CLICA_API int clica_mlp_bwd(int L, const int* widths, const float* const* W, con
                   int M, float slope, int mode, const void* packed_weights, int grads_prezeroed,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* Layers l_first, l_first-1, ..., l_last (L-1 >= l_first >= l_last >= 0) of the same backward chain; the
+ * gradient flowing between two consecutive range calls stays in `ws` (same workspace, same stream).
+ * clica_mlp_bwd == range(L-1 .. 0).  No reference analogue: the row-sharded multi-GPU step
+ * (semantics of main_3dident.py:373,480-492) issues the backward bucket by bucket so that the
+ * NCCL all-reduce of a finished layer's dW/db overlaps the differentiation of the earlier layers. */
+CLICA_API int clica_mlp_bwd_range(int L, const int* widths, const float* const* W, const float* const* acts,
+                  const float* g_out, float* const* dW, float* const* db, float* g_in,
+                  int M, float slope, int mode, const void* packed_weights, int grads_prezeroed,
+                  int l_first, int l_last, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam step.     replaces  torch.optim.Adam.step (main_mlp.py:283,312) for the
  *                                   encoder's parameter list; same update rule as torch's default
@@ -230,6 +240,12 @@ CLICA_API int clica_mixing_fwd(const float* x, int ldx, const float* const* W, i
  * Families: 0 loss fwd, 1 loss bwd, 2 loss finalize/prep/reduce, 3 tcgen05 GEMM, 4 CUDA-core GEMM,
  *           5 Adam, 6 misc (column sums, operand packing).
  * ---------------------------------------------------------------------------------------------- */
+/* The persistent tcgen05 GEMMs normally launch one CTA (or CTA pair) per SM.  clica_tc_set_sm_reserve(n) makes
+ * every later GEMM launch of this process leave n SMs free (0 <= n <= 64; default 0) -- the multi-GPU step sets it
+ * while NCCL's all-reduce of a finished gradient bucket runs concurrently with the remaining backward GEMMs.
+ * No reference analogue. */
+CLICA_API int clica_tc_set_sm_reserve(int sms);
+
 #define CLICA_NUM_FAMILIES 7
 CLICA_API long long clica_launch_count(int family);
 CLICA_API int clica_prof_enable(int on);

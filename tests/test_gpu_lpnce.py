@@ -223,3 +223,77 @@ def test_sharded_backward_equals_single_device(cuda_device):
         gmax = a.grad.abs().max().item()
         assert (g1 - a.grad[r * Bl:(r + 1) * Bl]).abs().max().item() <= 2e-5 * gmax
         assert (g2 - b.grad[r * Bl:(r + 1) * Bl]).abs().max().item() <= 2e-5 * gmax
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("roll", [False, True])
+def test_negative_and_signed_upstream_gradients(p, roll, cuda_device):
+    """(-loss).backward() and per-item weights of mixed sign: the backward coefficient E = 2 gl (1-alpha)/tau is then
+    negative, which the p = 1 gradient (w * sign(t)) must carry through (copysignf(w, t) dropped it)."""
+    from clica_b200 import functional as F
+    from oracle import c_oracle
+    B, M, d, tau = 260, 260 if roll else 333, 10, 0.8
+    rng = np.random.RandomState(100 + p + 10 * roll)
+    z1 = (rng.randn(B, d) * 0.6).astype(np.float32)
+    z2 = (z1 + 0.05 * rng.randn(B, d)).astype(np.float32)
+    z3 = np.roll(z1, 1, 0).copy() if roll else (rng.randn(M, d) * 0.6).astype(np.float32)
+    gl = rng.randn(B).astype(np.float32) / B                       # mixed signs
+    ref_w = c_oracle.lpnce(z1, z2, z3, p, tau, 0.5, include_pos=True, gl=gl)
+    ref_m = c_oracle.lpnce(z1, z2, z3, p, tau, 0.5, include_pos=True)
+    for mode in ("neg_mean", "weighted"):
+        a = torch.tensor(z1, device=cuda_device, requires_grad=True)
+        b = torch.tensor(z2, device=cuda_device, requires_grad=True)
+        n = torch.roll(a, 1, 0) if roll else torch.tensor(z3, device=cuda_device, requires_grad=True)
+        mean, per_item, _, _ = F.lp_infonce(a, b, n, float(p), tau, 0.5, True)
+        if mode == "neg_mean":
+            (-mean).backward()
+            ref, sgn = ref_m, -1.0
+        else:
+            (per_item * torch.tensor(gl, device=cuda_device)).sum().backward()
+            ref, sgn = ref_w, 1.0
+        g1 = sgn * ref["g1"]
+        if roll:
+            g1 = g1 + sgn * np.roll(ref["g3"], -1, 0)
+        gmax = float(np.abs(g1).max())
+        assert np.abs(a.grad.cpu().numpy() - g1).max() <= GRAD_TOL * gmax, (mode, p, roll)
+        assert np.abs(b.grad.cpu().numpy() - sgn * ref["g2"]).max() <= GRAD_TOL * gmax
+        if not roll:
+            assert np.abs(n.grad.cpu().numpy() - sgn * ref["g3"]).max() <= GRAD_TOL * gmax
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_sharded_backward_with_a_negative_scale(p, cuda_device):
+    """clica_lpnce_bwd_sharded with g_scale < 0 (the merged role weights w by E_i and E_j, both negative here)."""
+    from clica_b200 import sharded
+    from oracle import c_oracle
+    B, d, tau, W = 512, 10, 0.9, 2
+    rng = np.random.RandomState(50 + p)
+    z1n = (rng.randn(B, d) * 0.5).astype(np.float32)
+    z2n = (z1n + 0.05 * rng.randn(B, d)).astype(np.float32)
+    ref = c_oracle.lpnce(z1n, z2n, z1n, p, tau, 0.5, include_pos=True)       # z3 = all anchors (gathered)
+    g1_ref = -(ref["g1"] + ref["g3"])
+    z1, z2 = torch.tensor(z1n, device=cuda_device), torch.tensor(z2n, device=cuda_device)
+    Bl = B // W
+    stats, poss = [], []
+    for r in range(W):
+        _, _, pos, stat = sharded.local_forward(z1[r * Bl:(r + 1) * Bl], z2[r * Bl:(r + 1) * Bl], z1, float(p), tau, 0.5, True)
+        stats.append(stat.clone()), poss.append(pos.clone())
+    stat_all = torch.cat(stats)
+    scale = torch.tensor(-1.0, device=cuda_device)
+    gmax = float(np.abs(g1_ref).max())
+    for r in range(W):
+        g1, g2 = sharded.local_backward(z1[r * Bl:(r + 1) * Bl], z2[r * Bl:(r + 1) * Bl], z1, stat_all, poss[r],
+                                        r * Bl, float(p), tau, 0.5, True, g_scale=scale)
+        assert np.abs(g1.cpu().numpy() - g1_ref[r * Bl:(r + 1) * Bl]).max() <= GRAD_TOL * gmax
+        assert np.abs(g2.cpu().numpy() + ref["g2"][r * Bl:(r + 1) * Bl]).max() <= GRAD_TOL * gmax
+
+
+def test_integer_exponent_on_the_generic_kernels_p5(cuda_device):
+    """`--p 5` is reachable from the CLI (main_mlp.py:111-116, int): it runs on the generic ex2/lg2 kernels."""
+    g = load_golden("lpnce_roll_p5_generic_cpupin")
+    roll = bool(g["roll"])
+    out = _run(g["z1"], g["z2"], None if roll else g["z3"], float(g["p"]), float(g["tau"]), float(g["alpha"]),
+               bool(g["compat"]), cuda_device, gl=g["gl"] if "gl" in g else None, roll=roll)
+    ref = {k[:-3]: g[k] for k in g if k.endswith("_64")}
+    ref["loss_mean"], ref["pos_mean"], ref["neg_mean"] = float(ref["loss_mean"]), float(ref["pos_mean"]), float(ref["neg_mean"])
+    _check(out, ref, roll, grad_tol=3e-5)
