@@ -41,9 +41,9 @@ inline int plane_ld(int cols) { return (cols + 31) / 32 * 32; }
 int tc_split_planes(const float* src, int ld_src, int rows, int cols, float* hi, float* lo, int ld_dst,
                     cudaStream_t st);
 
-// EXPERIMENTAL (CLICA_PACK_FUSED=1; written after round 1's GPU budget was spent): the (hi, lo) planes of up to 8
-// matrices in ONE launch -- the encoder re-packs its five hidden weight matrices after every optimizer step, and five
-// 3 us launches cost more than the 5 MB they move
+// the (hi, lo) planes of up to 8 matrices in ONE launch (default; CLICA_PACK_FUSED=0: one launch per matrix) -- the
+// encoder re-packs its five hidden weight matrices after every optimizer step, and five 3 us launches cost more than
+// the 5 MB they move
 struct SplitJob { const float* src; int ld_src; int rows; int cols; float* hi; float* lo; int ld_dst; };
 int tc_split_planes_multi(const SplitJob* jobs, int n, cudaStream_t st);
 

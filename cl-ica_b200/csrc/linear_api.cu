@@ -238,7 +238,7 @@ PlanesIn weight_planes(const MlpPlan& p, const MlpWs& w, int l) {
     return a;
 }
 int pack_weights(const MlpPlan& p, const MlpWs& w, const float* const* W, cudaStream_t st) {
-    if (env_flag("CLICA_PACK_FUSED", 0) != 0) {      // EXPERIMENTAL: all eligible layers in one launch
+    if (env_flag("CLICA_PACK_FUSED", 1) != 0) {      // all eligible layers in one launch
         SplitJob jobs[64];
         int n = 0;
         for (int l = 0; l < p.L && l < 64; ++l) {

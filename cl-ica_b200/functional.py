@@ -402,7 +402,7 @@ def invalidate_packed_weights():
     _packed_cache.clear()
 
 
-# ---- frozen mixing network (EXPERIMENTAL: see include/clica.h, clica_mixing_fwd) ---------------------------
+# ---- frozen mixing network (see include/clica.h, clica_mixing_fwd) ------------------------------------------
 def mixing_plan(g):
     """(weights, slope) when ``g`` is the frozen mixing stack of invertible_network_utils.py:87-123 -- bias-free
     square ``nn.Linear`` layers with one LeakyReLU slope in between, nothing requiring grad -- else None."""

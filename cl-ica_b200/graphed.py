@@ -62,9 +62,9 @@ class GraphedTrainStep:
                 raise ValueError("GraphedTrainStep(group=...): LpSimCLRLoss(pow=False) is not implemented by the sharded CUDA loss")
             if float(criterion.p) < 1.0:
                 raise ValueError("GraphedTrainStep(group=...): p < 1 is not implemented by the sharded CUDA loss")
-        # EXPERIMENTAL (not yet run on a GPU, off by default): the frozen mixing net as one fused kernel
+        # the frozen mixing net as one fused kernel (CLICA_FUSED_MIXING=0: torch's L GEMMs + L-1 activations)
         self._mix = None
-        if g is not None and os.environ.get("CLICA_FUSED_MIXING", "0") == "1":
+        if g is not None and os.environ.get("CLICA_FUSED_MIXING", "1") == "1":
             self._mix = F.mixing_plan(g)
         self.optimizer = FusedAdam(params, lr=lr, betas=betas, eps=eps, capturable=True)
         dev = self.device

@@ -73,7 +73,13 @@ CLICA_API int         clica_device_info(int* sm_count, int* cc_major, int* cc_mi
  * use_pow  must be 1 (losses.py:452-454, `pow=True`, the only value any reference script uses).
  * ws       scratch of at least clica_lpnce_workspace_bytes(B, M, d) bytes, 16-byte aligned (split
  *          partials; dead after the call -- the backward is stateless and takes rowstat / pos back).
+ *          ZERO CONTRACT (all three loss entry points): the first CLICA_LPNCE_COUNTER_BYTES bytes of a loss
+ *          workspace hold arrival counters of the in-kernel split merge.  The caller zero-fills them ONCE
+ *          (e.g. when allocating the workspace); every call leaves them zero again, so a workspace can be
+ *          reused by consecutive calls on one stream without further memsets (and replayed from a CUDA graph).
+ * One kernel launch: pair walk, merge of the column splits, positive pair, per-item loss and the means.
  * ---------------------------------------------------------------------------------------------- */
+#define CLICA_LPNCE_COUNTER_BYTES 65536
 CLICA_API size_t clica_lpnce_workspace_bytes(int B, int M, int d);
 
 CLICA_API int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2, const float* z3, int ld3,
@@ -94,7 +100,8 @@ CLICA_API int clica_lpnce_fwd(const float* z1, int ld1, const float* z2, int ld2
  *             anchor-role term; a caller whose z3 aliases z1 (torch.roll, main_mlp.py:272) adds g_z3
  *             back through its own autograd graph exactly as the reference does.
  * Zero differences contribute exactly zero (torch's norm backward masks them).
- * ws: >= clica_lpnce_bwd_workspace_bytes(B, M, d) bytes.
+ * ws: >= clica_lpnce_bwd_workspace_bytes(B, M, d) bytes, zero contract as for the forward.
+ * g_loss_i == NULL (the training step): one kernel launch; otherwise three (coefficients, pair walk, reduce).
  * ---------------------------------------------------------------------------------------------- */
 CLICA_API size_t clica_lpnce_bwd_workspace_bytes(int B, int M, int d);
 
@@ -225,8 +232,8 @@ CLICA_API int clica_adam_step_capturable(int n, float* const* params, const floa
  *                                   LeakyReLU(slope) in between) for CUDA fp32 inputs: one kernel instead
  *                                   of L cuBLAS launches + L-1 elementwise launches.
  *   x [M, n] (ld ldx), W[l] = the l-th layer's [n, n] weight (out x in, contiguous), y [M, n] (ld ldy).
- *   Supported: 1 <= L <= 8, n <= 48, L*n*n*4 <= 48 KB.  EXPERIMENTAL in round 1: written after the round's
- *   GPU budget was spent, not yet run on a GPU; nothing calls it unless CLICA_FUSED_MIXING=1.
+ *   Supported: 1 <= L <= 8, n <= 48, L*n*n*4 <= 48 KB (validated on B200 in round 2: tests/test_gpu_kernels_r2.py;
+ *   GraphedTrainStep uses it for the mixing net unless CLICA_FUSED_MIXING=0).
  * ---------------------------------------------------------------------------------------------- */
 CLICA_API int clica_mixing_fwd(const float* x, int ldx, const float* const* W, int L, int n, int M, float slope,
                      float* y, int ldy, void* stream);
