@@ -346,6 +346,55 @@ class Ctx:
     pass
 
 
+def family_of(kernel_name):
+    n = kernel_name
+    if "lpnce_fwd" in n:
+        return "loss_fwd"
+    if "lpnce_bwd" in n:
+        return "loss_bwd"
+    if "lpnce_" in n:
+        return "loss_aux"
+    if "gemm_tc_kernel" in n:
+        return "gemm_tc"
+    if "skinny" in n or "gemm_simt" in n or "mixing" in n:
+        return "gemm_simt"
+    if "adam" in n:
+        return "adam"
+    if "split_planes" in n or "colsum" in n or "sampler" in n:
+        return "misc"
+    if "nccl" in n.lower():
+        return "nccl"
+    if "memcpy" in n.lower() or "memset" in n.lower():
+        return "memops"
+    return "torch_other"
+
+
+def profile_families(step_fn, k):
+    """Per-family kernel time (ms per step) and launches per step from CUPTI kernel records of k calls of step_fn."""
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(k):
+            step_fn()
+        torch.cuda.synchronize()
+    ms = {name: 0.0 for name in FAMILIES + ["nccl", "torch_other", "memops"]}
+    cnt = {name: 0 for name in ms}
+    seen = 0
+    for ev in prof.events():
+        dt = getattr(ev, "device_time_total", None)
+        if dt is None:
+            dt = getattr(ev, "cuda_time_total", 0.0)
+        if str(getattr(ev, "device_type", "")).endswith("CUDA") and dt and dt > 0:
+            fam = family_of(ev.name)
+            ms[fam] += dt / 1e3
+            cnt[fam] += 1
+            seen += 1
+    if seen == 0:
+        raise RuntimeError("no CUDA kernel records")
+    return {a: b / k for a, b in ms.items()}, {a: b // k for a, b in cnt.items()}
+
+
 def measure_workload(cx, wl_name, scaling, steps, warmup, full):
     """Times one workload on the ranks of `cx`; returns a dict (rank 0 uses it).  `full` adds the eager drop-in e2e."""
     import torch
@@ -470,25 +519,36 @@ def measure_workload(cx, wl_name, scaling, steps, warmup, full):
     value = B_global / (ms_step * 1e-3)
     loss_value = float(last.item())
 
-    # ---- per-kernel-family device time (CUDA events inside the library around its own launches) --------
-    # Events cannot bracket kernels inside a graph, so this is an eager pass of the same step.  Each profiled step
-    # is queued behind a ~4 ms device-side spin: the host gets ahead, the launches sit back to back in the stream and
-    # an event pair measures its kernel, not the host's launch gaps.
-    import ctypes
-    prof_steps = min(steps, 10)
-    spin = int(4e-3 * 1.9e9)
-    step_eager()
-    _lib.check(lib.clica_prof_enable(1), "clica_prof_enable")
-    for _ in range(prof_steps):
-        torch.cuda._sleep(spin)
+    # ---- per-kernel-family device time ---------------------------------------------------------------
+    # Preferred: CUPTI kernel records (torch.profiler) of the SAME graph replays that were timed -- exact per-kernel
+    # durations inside the timed step flavour, torch's own kernels and NCCL included.  Fallback (profiler unavailable,
+    # e.g. when the whole process runs under ncu): the library's CUDA events around its own launches in an eager pass
+    # queued behind a device-side spin (kernel time without host launch gaps; ~3 us of event overhead per launch).
+    fam_ms, fam_n, fam_src = None, None, None
+    try:
+        fam_ms, fam_n = profile_families(step_device, min(steps, 10))
+        fam_src = "torch.profiler (CUPTI) kernel records of the timed step flavour (" + step_mode.split(" ")[0] + ")"
+    except Exception as exc:
+        sys.stderr.write(f"bench.py: torch.profiler breakdown unavailable ({exc!r}); using library events\n")
+    if fam_ms is None:
+        import ctypes
+        prof_steps = min(steps, 10)
+        spin = int(4e-3 * 1.9e9)
         step_eager()
-        torch.cuda.synchronize()
-    ms_f = (ctypes.c_float * 7)()
-    n_f = (ctypes.c_int * 7)()
-    _lib.check(lib.clica_prof_collect(ms_f, n_f), "clica_prof_collect")
-    lib.clica_prof_enable(0)
-    fam_ms = {name: ms_f[i] / prof_steps for i, name in enumerate(FAMILIES)}
-    fam_n = {name: n_f[i] // prof_steps for i, name in enumerate(FAMILIES)}
+        _lib.check(lib.clica_prof_enable(1), "clica_prof_enable")
+        for _ in range(prof_steps):
+            torch.cuda._sleep(spin)
+            step_eager()
+            torch.cuda.synchronize()
+        ms_f = (ctypes.c_float * 7)()
+        n_f = (ctypes.c_int * 7)()
+        _lib.check(lib.clica_prof_collect(ms_f, n_f), "clica_prof_collect")
+        lib.clica_prof_enable(0)
+        fam_ms = {name: ms_f[i] / prof_steps for i, name in enumerate(FAMILIES)}
+        fam_n = {name: n_f[i] // prof_steps for i, name in enumerate(FAMILIES)}
+        fam_ms.update(nccl=0.0, torch_other=0.0, memops=0.0)
+        fam_n.update(nccl=0, torch_other=0, memops=0)
+        fam_src = "library CUDA events around each launch, eager pass behind a device-side spin"
 
     # ---- e2e: host buffers, H2D every step, loss read back every step -----------------------------------
     def time_e2e(fn):
@@ -546,7 +606,7 @@ def measure_workload(cx, wl_name, scaling, steps, warmup, full):
     work = algorithmic_work(wl, B_local, B_global, world)
     res = dict(wl=wl, B_local=B_local, B_global=B_global, ms_per_step=ms_step, value=value, loss=loss_value,
                step_mode=step_mode, launches=int(launches), launches_per_step=launches / steps,
-               fam_ms=fam_ms, fam_n=fam_n, work=work,
+               fam_ms=fam_ms, fam_n=fam_n, fam_src=fam_src, work=work,
                e2e={"value": B_global / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 2 * B_local * n * 4, "d2h_bytes_per_step": 12, "api": e2e_mode})
     if e2e_eager_ms is not None:
@@ -576,11 +636,11 @@ def kernel_report(res, sm_count, f_sm, peaks, fp32_probe):
                            "gbs": work["loss_bytes"] / (loss_ms * 1e-3) / 1e9 if loss_ms > 0 else None,
                            "frac_of_hbm_peak": work["loss_bytes"] / (loss_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if loss_ms > 0 else None},
         "adam_ms": fam_ms["adam"], "loss_aux_ms": fam_ms["loss_aux"], "misc_ms": fam_ms["misc"],
+        "nccl_ms": fam_ms.get("nccl", 0.0), "torch_other_ms": fam_ms.get("torch_other", 0.0), "memops_ms": fam_ms.get("memops", 0.0),
         "sum_ms": total, "fp32_pipe_clock_mhz": f_sm / 1e6,
         "fp32_pipe_peak_source": ("profiles/r2_fp32_pipe_probe.json (FFMA microbenchmark), scaled to the sampled clock"
                                   if fp32_probe and fp32_probe.get("lane_ops_per_s") else "nominal SMs x 128 lanes x clock"),
-        "timing": "library CUDA events around each launch in an eager pass queued behind a device-side spin "
-                  "(kernel time without host launch gaps); torch's own kernels (mixing net, roll, cat) are not in any family",
+        "timing": res.get("fam_src"),
     }
 
 

@@ -20,7 +20,7 @@
 //   workspace) merges the split partials of its rows in a fixed order -- per-item loss, row statistics and the
 //   three means in the forward; the summed gradient plus the positive-pair term in the backward -- so the forward
 //   is ONE launch and the backward is ONE launch, and results are deterministic.
-//   p = 2 additionally has a "dot form" of the distance on centred data (see below): half the instructions.
+//   p = 2 additionally has a "dot form" of the distance (see below): half the instructions, guarded by a norm bound.
 #pragma once
 #include "common.cuh"
 
@@ -40,7 +40,7 @@ constexpr size_t kCounterBytes = CLICA_LPNCE_COUNTER_BYTES;
 constexpr int kMaxRowTilesFwd = (int)(kCounterBytes / 4) - 4;
 constexpr int kMaxRowTilesBwd = (int)(kCounterBytes / 8);      // per role
 
-// P == 2 with one lane per pair: the distance may be evaluated in "dot form" on centred data (see lpnce_fwd_kernel)
+// P == 2 with one lane per pair: the distance may be evaluated in "dot form" (see half_norm_of_row)
 constexpr bool dot_capable(int P, int F) { return P == 2 && F == 1; }
 
 // rows owned per thread: 2 while the register budget allows it; the dot form (p = 2, d <= 10) has so little work per
@@ -53,9 +53,9 @@ constexpr int rows_per_cta(int R, int F = 1) { return (32 / F) * R * (kWarps / k
 constexpr int slice_floats(int DP, int F) { return 2 * DP + (F > 1 ? 4 : 0); }
 constexpr int row_floats(int DP, int F) { return F * slice_floats(DP, F); }
 constexpr int tile_rows(int F) { return kTN / F; }
-// per-stage floats: features (+ (|b|^2/2, 0) per row for the dot form) / + (m2, ls, E, |b|^2/2) per row (backward)
-constexpr int fwd_stage_floats(int DP, int F) { return tile_rows(F) * row_floats(DP, F) + 2 * tile_rows(F); }
-constexpr int bwd_stage_floats(int DP, int F) { return tile_rows(F) * row_floats(DP, F) + 4 * tile_rows(F); }
+// per-stage floats
+constexpr int fwd_stage_floats(int DP, int F) { return tile_rows(F) * row_floats(DP, F); }
+constexpr int bwd_stage_floats(int DP, int F) { return tile_rows(F) * row_floats(DP, F) + 4 * tile_rows(F); }   // + (m2, ls, E, -) per row
 
 inline size_t fwd_smem_bytes(int DP, int R, int F = 1) {
     size_t tiles = 2ull * fwd_stage_floats(DP, F) * sizeof(float);
@@ -286,45 +286,24 @@ __device__ __forceinline__ float dabs_pow(float t, float p) {   // 0 at t == 0 (
 }
 
 // ---- dot form (p = 2, one lane per pair) -------------------------------------------------------------
-// |a - b|^2 / 2 = |a'|^2/2 + |b'|^2/2 - a'.b' with a' = a - c, b' = b - c: five packed FMAs per pair at d = 10 instead of
-// five packed subtractions + five packed FMAs, and the per-row half norms ride along (owner: a register; streamed: one
-// float per row, computed when the tile is centred in shared memory).  Centring by c = the mean of the first 32
-// streamed rows keeps the cancellation in  |a'|^2 + |b'|^2 - 2a'.b'  proportional to the SPREAD of the rows, not to
-// their common offset (an untrained encoder maps every input to almost the same point).  The form is used tile by
-// tile while coef * (|a'|^2 + max_j |b'_j|^2) <= dot_limit (8), which bounds the logit's absolute error (measured by
-// fp32 emulation: <= ~2.5e-7 * that bound, rms 6x smaller; unit-sphere outputs at tau = 1 sit at 3.6) and its range
-// (no re-scaling needed); any other tile takes the subtract-then-square loop on the same centred data.
-// c = mean of the first min(32, MS) streamed rows: every CTA (and every warp) computes the same vector, lane l loading
-// row l; for rows spread around a common centre this is within ~1/sqrt(32) of it, so |a'|^2, |b'|^2 measure the spread
+// |a - b|^2 / 2 = |a|^2/2 + |b|^2/2 - a.b : five packed FMAs per pair at d = 10 instead of five packed subtractions +
+// five packed FMAs, and the half norms ride along (owner: a register; streamed: one float per row, computed by each
+// warp for the 32 rows of the tile it is about to walk).  The cancellation error of the form is ~1e-7 * (|a|^2 + |b|^2)
+// in D, so it is used -- warp by warp, tile by tile -- only while  coef * (|a|^2 + max_j |b_j|^2) <= dot_limit (8):
+// measured by fp32 emulation the logit's absolute error is then <= ~2.5e-7 * that bound (rms 6x smaller; unit-sphere
+// outputs at tau = 1 sit at 2.9), and every logit lies in [-2 * dot_limit, 0] so no re-scaling can be needed.  Every
+// other (warp, tile) takes the subtract-then-square loop, which is exact for coincident rows and has no cancellation.
+// Returns |row|^2 / 2 of this lane's streamed row of the warp's slice (0 for rows past the valid count).
 template <int DP>
-__device__ __forceinline__ void load_centre(float2 (&cen)[DP], const float* __restrict__ S, int ldS, int MS, int d, int lane) {
-    const int n = MS < 32 ? MS : 32;
-    const float inv = 1.f / (float)n;
-#pragma unroll
-    for (int c = 0; c < DP; ++c) {
-        float v0 = (lane < n && 2 * c < d) ? __ldg(S + (size_t)lane * ldS + 2 * c) : 0.f;
-        float v1 = (lane < n && 2 * c + 1 < d) ? __ldg(S + (size_t)lane * ldS + 2 * c + 1) : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-        }
-        cen[c] = make_float2(v0 * inv, v1 * inv);
-    }
-}
-// centre the rows of a landed tile in place (thread t < kTN handles row t) and return |b'|^2 / 2 of that row
-template <int DP>
-__device__ __forceinline__ float centre_row(float* tile_row, const float2 (&cen)[DP]) {
-    float2* row = reinterpret_cast<float2*>(tile_row);
+__device__ __forceinline__ float half_norm_of_row(const float* tile_row, bool valid) {
+    const float2* row = reinterpret_cast<const float2*>(tile_row);
     float h0 = 0.f, h1 = 0.f;
 #pragma unroll
     for (int c = 0; c < DP; ++c) {
-        float2 v = row[c];
-        v.x -= cen[c].x; v.y -= cen[c].y;
-        row[c] = v;
+        const float2 v = row[c];
         h0 = fmaf(v.x, v.x, h0); h1 = fmaf(v.y, v.y, h1);
     }
-    return 0.5f * (h0 + h1);
+    return valid ? 0.5f * (h0 + h1) : 0.f;
 }
 
 // ================================ forward ==========================================================
@@ -350,19 +329,15 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
 
     float2 na[R][DP];
     load_owner_rows<DP, R, F>(na, q.O, q.ldO, q.BO, q.d, row_base, lane);
-    float2 cen[DOT ? DP : 1];
     float ha[R];
     const bool dot_on = DOT && q.dot_limit > 0.f;
+    __shared__ __align__(16) float2 hbw[DOT ? kWarps : 1][32];   // per warp: (|b|^2/2, 0) of its 32 streamed rows of the tile
     if constexpr (DOT) {
-        load_centre<DP>(cen, q.S, q.ldS, q.MS, q.d, lane);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float h0 = 0.f, h1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < DP; ++c) {
-                if (dot_on) { na[r][c].x += cen[c].x; na[r][c].y += cen[c].y; }     // -(a - c)
-                h0 = fmaf(na[r][c].x, na[r][c].x, h0); h1 = fmaf(na[r][c].y, na[r][c].y, h1);
-            }
+            for (int c = 0; c < DP; ++c) { h0 = fmaf(na[r][c].x, na[r][c].x, h0); h1 = fmaf(na[r][c].y, na[r][c].y, h1); }
             ha[r] = 0.5f * (h0 + h1);
         }
     }
@@ -387,17 +362,8 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
             cp_async_wait<0>();
         }
         __syncthreads();
-        float* tile = smem + stage * STAGE;
+        const float* tile = smem + stage * STAGE;
         const int nvalid = min(TNF, q.MS - t * TNF);
-        if constexpr (DOT) {
-            if (dot_on) {
-                if (tid < TNF) {
-                    const float h = centre_row<DP>(tile + tid * TW, cen);
-                    *reinterpret_cast<float2*>(tile + TNF * TW + 2 * tid) = make_float2(tid < nvalid ? h : 0.f, 0.f);
-                }
-                __syncthreads();
-            }
-        }
         if (t == t0) {
             // reference point of the lazy soft-max: the logit of the first streamed row of this split
             const float2* b = reinterpret_cast<const float2*>(tile + fs * slice_floats(DP, F));
@@ -413,13 +379,19 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
         bool use_dot = false;
         if constexpr (DOT) {
             if (dot_on) {
-                // warp-uniform decision for this warp's CPW streamed rows of the tile
-                float hb = (cw * CPW + lane < TNF) ? tile[TNF * TW + 2 * (cw * CPW + lane)] : 0.f;
+                // warp-uniform decision for this warp's CPW (= 32) streamed rows of the tile
+                static_assert(!DOT || CPW == 32, "one streamed row per lane");
+                const int jrow = cw * CPW + lane;
+                const float h = half_norm_of_row<DP>(tile + jrow * TW, jrow < nvalid);
+                __syncwarp();                                   // the previous tile's readers of hbw are done
+                hbw[warp][lane] = make_float2(h, 0.f);
+                float hb = h;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) hb = fmaxf(hb, __shfl_xor_sync(0xffffffffu, hb, o));
                 bool ok = true;
 #pragma unroll
                 for (int r = 0; r < R; ++r) ok = ok && (2.f * q.coef * (ha[r] + hb) <= q.dot_limit) && (m[r] >= kDotFloor);
+                __syncwarp();
                 use_dot = __all_sync(0xffffffffu, ok);
             }
         }
@@ -429,11 +401,11 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
                 float ci[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) ci[r] = fmaf(K, ha[r], -m[r]);
-                const float4* hbv = reinterpret_cast<const float4*>(tile + TNF * TW);
+                const float4* hbv = reinterpret_cast<const float4*>(&hbw[warp][0]);
                 for (int kk = cw * CPW; kk < c_end; kk += 2) {
                     float2 bb[2 * DP];
                     load_pair_rows<DP, F>(bb, tile, kk, fs);
-                    const float4 h2 = hbv[kk >> 1];               // (|b_kk|^2/2, 0, |b_kk+1|^2/2, 0)
+                    const float4 h2 = hbv[(kk - cw * CPW) >> 1];  // (|b_kk|^2/2, 0, |b_kk+1|^2/2, 0)
                     const bool has1 = (kk + 1 < c_end);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -649,19 +621,15 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         eo[r] = 0.f;
         if (merged && row < ro.BO) eo[r] = q.fused ? E_u : __ldg(ro.EO + row);
     }
-    float2 cen[DOT ? DP : 1];
     float ha[R], wsum[R];
     const bool dot_on = DOT && q.dot_limit > 0.f;
+    __shared__ __align__(16) float2 hbw[DOT ? kWarps : 1][32];   // per warp: (|b|^2/2, 0) of its 32 streamed rows of the tile
     if constexpr (DOT) {
-        load_centre<DP>(cen, ro.S, ro.ldS, ro.MS, q.d, lane);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float h0 = 0.f, h1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < DP; ++c) {
-                if (dot_on) { na[r][c].x += cen[c].x; na[r][c].y += cen[c].y; }
-                h0 = fmaf(na[r][c].x, na[r][c].x, h0); h1 = fmaf(na[r][c].y, na[r][c].y, h1);
-            }
+            for (int c = 0; c < DP; ++c) { h0 = fmaf(na[r][c].x, na[r][c].x, h0); h1 = fmaf(na[r][c].y, na[r][c].y, h1); }
             ha[r] = 0.5f * (h0 + h1);
             wsum[r] = 0.f;
         }
@@ -695,28 +663,25 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         if (t + 1 < t1) { issue_tile(stage ^ 1, t + 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
-        float* tile = smem + stage * STAGE;
+        const float* tile = smem + stage * STAGE;
         const float4* ss = reinterpret_cast<const float4*>(tile + TNF * TW);
         const int nvalid = min(TNF, ro.MS - t * TNF);
-        if constexpr (DOT) {
-            if (dot_on) {
-                if (tid < TNF) {
-                    const float h = centre_row<DP>(tile + tid * TW, cen);
-                    tile[TNF * TW + 4 * tid + 3] = tid < nvalid ? h : 0.f;
-                }
-                __syncthreads();
-            }
-        }
         const int c_end = min(cw * CPW + CPW, nvalid);
         bool use_dot = false;
         if constexpr (DOT) {
             if (dot_on) {
-                float hb = (cw * CPW + lane < TNF) ? tile[TNF * TW + 4 * (cw * CPW + lane) + 3] : 0.f;
+                static_assert(!DOT || CPW == 32, "one streamed row per lane");
+                const int jrow = cw * CPW + lane;
+                const float h = half_norm_of_row<DP>(tile + jrow * TW, jrow < nvalid);
+                __syncwarp();
+                hbw[warp][lane] = make_float2(h, 0.f);
+                float hb = h;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) hb = fmaxf(hb, __shfl_xor_sync(0xffffffffu, hb, o));
                 bool ok = true;
 #pragma unroll
                 for (int r = 0; r < R; ++r) ok = ok && (2.f * q.coef * (ha[r] + hb) <= q.dot_limit);
+                __syncwarp();
                 use_dot = __all_sync(0xffffffffu, ok);
             }
         }
@@ -724,21 +689,19 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
             float2 bb[2 * DP];
             load_pair_rows<DP, F>(bb, tile, kk, fs);
             const bool has1 = (kk + 1 < c_end);
-            float sm0 = 0.f, sm1 = 0.f, sl0 = 0.f, sl1 = 0.f, es0 = es_u, es1 = has1 ? es_u : 0.f, hb0 = 0.f, hb1 = 0.f;
-            if (has_ss || DOT) {
-                const float4 s0 = ss[kk], s1 = ss[kk + 1];   // (m2, ls, ES, |b|^2/2)
-                if (has_ss) {
-                    sm0 = s0.x; sl0 = s0.y; sm1 = s1.x; sl1 = s1.y;
-                    if (es_array) { es0 = s0.z; es1 = has1 ? s1.z : 0.f; }
-                }
-                hb0 = s0.w; hb1 = s1.w;
+            float sm0 = 0.f, sm1 = 0.f, sl0 = 0.f, sl1 = 0.f, es0 = es_u, es1 = has1 ? es_u : 0.f;
+            if (has_ss) {
+                const float4 s0 = ss[kk], s1 = ss[kk + 1];   // (m2, ls, ES, -)
+                sm0 = s0.x; sl0 = s0.y; sm1 = s1.x; sl1 = s1.y;
+                if (es_array) { es0 = s0.z; es1 = has1 ? s1.z : 0.f; }
             }
             if (use_dot) {
                 if constexpr (DOT) {
                     const float K = -2.f * q.coef;
+                    const float4 h2 = reinterpret_cast<const float4*>(&hbw[warp][0])[(kk - cw * CPW) >> 1];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        float2 a0 = make_float2(hb0, 0.f), a1 = make_float2(hb1, 0.f);
+                        float2 a0 = make_float2(h2.x, h2.y), a1 = make_float2(h2.z, h2.w);
 #pragma unroll
                         for (int c = 0; c < DP; ++c) {
                             a0 = __ffma2_rn(bb[c], na[r][c], a0);
@@ -795,7 +758,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         __syncthreads();
     }
     if constexpr (DOT) {
-        // dot-form tiles accumulated sum_j w_j b'_j: complete them to sum_j w_j (b'_j - a') with na = -a'
+        // dot-form tiles accumulated sum_j w_j b_j: complete them to sum_j w_j (b_j - a) with na = -a
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float2 wv = make_float2(wsum[r], wsum[r]);
