@@ -53,6 +53,8 @@ SIGNATURES = {
     "clica_mlp_bwd_range": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_float, _c_int, _vp, _c_int,
                                      _c_int, _c_int, _vp, _c_size_t, _vp]),
     "clica_mixing_fwd": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_float, _vp, _c_int, _vp]),
+    "clica_sample_latents": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _c_float,
+                                      _c_float, _c_float, _c_float, ctypes.c_uint64, ctypes.c_uint64, _vp]),
     "clica_tc_set_sm_reserve": (_c_int, [_c_int]),
     "clica_launch_count": (ctypes.c_longlong, [_c_int]),
     "clica_prof_enable": (_c_int, [_c_int]),

@@ -37,7 +37,7 @@ struct ReduceParams {
     const float* E; const float* CP;          // CP nullable (no positive term)
     const float* z1; int ld1; const float* z2; int ld2;
     float* g_out; int ldg; float* g_z2; int ldg2;   // both nullable
-    int rows; int d; int TW; float p;
+    int rows; int d; int TW; float p; int sim;
 };
 __global__ void lpnce_reduce_kernel(const ReduceParams q) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,11 +54,17 @@ __global__ void lpnce_reduce_kernel(const ReduceParams q) {
         for (int s = 0; s < q.nsB; ++s) b += q.partB[((size_t)s * q.rowsB + row) * q.TW + c];
         g += b;
     }
-    g *= q.p;
+    if (!q.sim) g *= q.p;
     if (q.CP) {
-        const float gp = q.CP[row] * dabs_pow(q.z1[(size_t)row * q.ld1 + c] - q.z2[(size_t)row * q.ld2 + c], q.p);
-        g += gp;
-        if (q.g_z2) q.g_z2[(size_t)row * q.ldg2 + c] = -gp;
+        const float ov = q.z1[(size_t)row * q.ld1 + c], zv = q.z2[(size_t)row * q.ld2 + c];
+        if (q.sim) {
+            g -= q.CP[row] * zv;
+            if (q.g_z2) q.g_z2[(size_t)row * q.ldg2 + c] = -q.CP[row] * ov;
+        } else {
+            const float gp = q.CP[row] * dabs_pow(ov - zv, q.p);
+            g += gp;
+            if (q.g_z2) q.g_z2[(size_t)row * q.ldg2 + c] = -gp;
+        }
     }
     if (q.g_out) q.g_out[(size_t)row * q.ldg + c] = g;
 }
@@ -76,6 +82,7 @@ Shape pick_shape(int d) {
     return Shape{-1, 0};
 }
 int p_code(float p) {
+    if (p == 0.f) return kSim;        // dot-product similarity (SimCLRLoss; main_mlp.py selects it with --p 0)
     if (p == 1.f) return 1;
     if (p == 2.f) return 2;
     if (p == 3.f) return 3;
@@ -104,6 +111,7 @@ int occ_fwd(int pc, Shape sh, int r4) {
         case 2: n = occ_fwd_p2(sh.DP, sh.F, r4); break;
         case 3: n = occ_fwd_p3(sh.DP, sh.F, r4); break;
         case 4: n = occ_fwd_p4(sh.DP, sh.F, r4); break;
+        case 5: n = occ_fwd_p5(sh.DP, sh.F, r4); break;
         default: n = occ_fwd_p0(sh.DP, sh.F, r4); break;
     }
     return n < 1 ? 1 : n;
@@ -115,6 +123,7 @@ int occ_bwd(int pc, Shape sh) {
         case 2: n = occ_bwd_p2(sh.DP, sh.F); break;
         case 3: n = occ_bwd_p3(sh.DP, sh.F); break;
         case 4: n = occ_bwd_p4(sh.DP, sh.F); break;
+        case 5: n = occ_bwd_p5(sh.DP, sh.F); break;
         default: n = occ_bwd_p0(sh.DP, sh.F); break;
     }
     return n < 1 ? 1 : n;
@@ -126,6 +135,9 @@ int occ_bwd(int pc, Shape sh) {
 int fwd_r4_enabled() { return env_flag("CLICA_LPNCE_R4", 1) != 0; }
 // dot-form bound (see lpnce_kernels.cuh); CLICA_LPNCE_DOT=0 disables the form
 float dot_limit() { return env_flag("CLICA_LPNCE_DOT", 1) != 0 ? 8.0f : 0.f; }
+// backward: measured on B200 (profiles/r2_loss_probe.md) the dot form is SLOWER there than subtract-then-square (the
+// weights need both operands anyway and the kernel is latency-bound at 16 warps per SM), so it is opt-in
+float dot_limit_bwd() { return env_flag("CLICA_LPNCE_DOT_BWD", 0) != 0 ? dot_limit() : 0.f; }
 bool r4_applies(int pc, Shape sh) { return pc == 2 && sh.F == 1 && fwd_rows_per_thread(sh.DP, true) != fwd_rows_per_thread(sh.DP, false); }
 SplitPlan plan_fwd(int B, int M, Shape sh, int sms, int r4) {
     const int R = fwd_rows_per_thread(sh.DP, r4 != 0);
@@ -142,6 +154,7 @@ int dispatch_fwd(int pc, Shape sh, const FwdParams& q, dim3 g, cudaStream_t s, i
         case 2: return launch_fwd_p2(sh.DP, sh.F, q, g, s, r4);
         case 3: return launch_fwd_p3(sh.DP, sh.F, q, g, s, r4);
         case 4: return launch_fwd_p4(sh.DP, sh.F, q, g, s, r4);
+        case 5: return launch_fwd_p5(sh.DP, sh.F, q, g, s, r4);
         default: return launch_fwd_p0(sh.DP, sh.F, q, g, s, r4);
     }
 }
@@ -151,6 +164,7 @@ int dispatch_bwd(int pc, Shape sh, const BwdParams& q, dim3 g, cudaStream_t s) {
         case 2: return launch_bwd_p2(sh.DP, sh.F, q, g, s);
         case 3: return launch_bwd_p3(sh.DP, sh.F, q, g, s);
         case 4: return launch_bwd_p4(sh.DP, sh.F, q, g, s);
+        case 5: return launch_bwd_p5(sh.DP, sh.F, q, g, s);
         default: return launch_bwd_p0(sh.DP, sh.F, q, g, s);
     }
 }
@@ -158,8 +172,8 @@ int dispatch_bwd(int pc, Shape sh, const BwdParams& q, dim3 g, cudaStream_t s) {
 int check_common(int B, int M, int d, float p, float tau, int use_pow, Shape* sh, DeviceInfo* di) {
     CLICA_REQUIRE(B >= 1 && M >= 1 && d >= 1, CLICA_E_BADARG, "lpnce: need B, M, d >= 1 (got %d, %d, %d)", B, M, d);
     CLICA_REQUIRE(tau > 0.f, CLICA_E_BADARG, "lpnce: tau must be > 0 (got %g)", (double)tau);
-    CLICA_REQUIRE(p >= 1.f, CLICA_E_UNSUPPORTED,
-                  "lpnce: p = %g < 1 (losses.py:433-442 branch) is not implemented by the CUDA path", (double)p);
+    CLICA_REQUIRE(p >= 1.f || p == 0.f, CLICA_E_UNSUPPORTED,
+                  "lpnce: 0 < p = %g < 1 (losses.py:433-442 branch) is not implemented by the CUDA path", (double)p);
     CLICA_REQUIRE(use_pow == 1, CLICA_E_UNSUPPORTED, "lpnce: pow=False is not implemented by the CUDA path");
     *sh = pick_shape(d);
     CLICA_REQUIRE(sh->DP > 0, CLICA_E_UNSUPPORTED, "lpnce: feature width d = %d > 320 is not implemented", d);
@@ -309,7 +323,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         q.d = d; q.coef = kLog2e / tau; q.pg = p; q.nroles = 0;
         q.tau = tau; q.alpha = alpha; q.include_pos = include_pos;
         q.fused = fused ? 1 : 0; q.g_mean = g_mean; q.default_g = 0.f; q.inv_count = 1.f / (float)B;
-        q.dot_limit = dot_capable(pc, sh.F) ? dot_limit() : 0.f;
+        q.dot_limit = dot_capable(pc, sh.F) ? dot_limit_bwd() : 0.f;
         init_role(q.role[0]); init_role(q.role[1]);
         int gx = 0, gy = 0;
         if (needA) {   // anchors own, negatives stream
@@ -341,7 +355,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         r.partB = nullptr; r.nsB = 0; r.rowsB = 0;
         r.E = w.E; r.CP = w.CP; r.z1 = z1; r.ld1 = ld1; r.z2 = z2; r.ld2 = ld2;
         r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
-        r.rows = B; r.d = d; r.TW = TW; r.p = p;
+        r.rows = B; r.d = d; r.TW = TW; r.p = p; r.sim = (pc == kSim) ? 1 : 0;
         const long long n = (long long)B * d;
         { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
         CLICA_CUDA_OK(cudaGetLastError());
@@ -352,7 +366,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         r.partB = w.partB; r.nsB = pb.nsplit; r.rowsB = M;
         r.E = nullptr; r.CP = nullptr; r.z1 = nullptr; r.ld1 = 0; r.z2 = nullptr; r.ld2 = 0;
         r.g_out = g_z3; r.ldg = ldg3; r.g_z2 = nullptr; r.ldg2 = 0;
-        r.rows = M; r.d = d; r.TW = TW; r.p = p;
+        r.rows = M; r.d = d; r.TW = TW; r.p = p; r.sim = (pc == kSim) ? 1 : 0;
         const long long n = (long long)M * d;
         { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
         CLICA_CUDA_OK(cudaGetLastError());
@@ -400,7 +414,7 @@ extern "C" int clica_lpnce_bwd_sharded(const float* z1_local, int ld1, const flo
     q.d = d; q.coef = kLog2e / tau; q.pg = p; q.nroles = 1;
     q.tau = tau; q.alpha = alpha; q.include_pos = include_pos;
     q.fused = 1; q.g_mean = g_scale; q.default_g = 1.f; q.inv_count = 1.f / (float)M;
-    q.dot_limit = dot_capable(pc, sh.F) ? dot_limit() : 0.f;
+    q.dot_limit = dot_capable(pc, sh.F) ? dot_limit_bwd() : 0.f;
     init_role(q.role[0]); init_role(q.role[1]);
     {
         BwdRole& r = q.role[0];

@@ -128,7 +128,8 @@ struct BwdParams {
 #ifdef __CUDACC__
 
 // ---- per-exponent arithmetic ----------------------------------------------------------------------
-// P = 1,2,3,4: multiply-only; P = 0: generic real exponent through lg2/ex2 (pg = p).
+// P = 1,2,3,4: multiply-only; P = 0: generic real exponent through lg2/ex2 (pg = p); P = kSim: dot-product similarity.
+constexpr int kSim = 5;
 template <int P>
 struct Lp {
     // acc += |t|^p for the two features packed in t
@@ -177,6 +178,17 @@ struct Lp {
             g.y = fmaf(w, copysignf(ay, t.y), g.y);
             return g;
         }
+    }
+    // pair forms: b = two features of the streamed row, na = the NEGATED features of the owner row.
+    // P = kSim (dot-product similarity, the reference's SimCLRLoss, losses.py:186): the "distance" is D = -a.b, so that
+    // the logit -D/tau = a.b/tau and everything downstream (soft-max, weights, -dD/d owner = b) is shared with the Lp family
+    static __device__ __forceinline__ float2 pair_acc(float2 b, float2 na, float2 acc, float pg) {
+        if constexpr (P == kSim) return __ffma2_rn(b, na, acc);
+        else return accum(__fadd2_rn(b, na), acc, pg);
+    }
+    static __device__ __forceinline__ float2 pair_grad(float w, float2 b, float2 na, float2 g, float pg) {
+        if constexpr (P == kSim) return __ffma2_rn(make_float2(w, w), b, g);
+        else return grad(w, __fadd2_rn(b, na), g, pg);
     }
 };
 
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
             for (int r = 0; r < R; ++r) {
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < DP; ++c) acc = Lp<P>::accum(__fadd2_rn(b[c], na[r][c]), acc, q.pg);
+                for (int c = 0; c < DP; ++c) acc = Lp<P>::pair_acc(b[c], na[r][c], acc, q.pg);
                 m[r] = -slice_sum<F>(acc.x + acc.y) * q.coef;
             }
         }
@@ -431,8 +443,8 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
                     float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int c = 0; c < DP; ++c) {
-                        a0 = Lp<P>::accum(__fadd2_rn(bb[c], na[r][c]), a0, q.pg);
-                        a1 = Lp<P>::accum(__fadd2_rn(bb[DP + c], na[r][c]), a1, q.pg);
+                        a0 = Lp<P>::pair_acc(bb[c], na[r][c], a0, q.pg);
+                        a1 = Lp<P>::pair_acc(bb[DP + c], na[r][c], a1, q.pg);
                     }
                     const float D0 = slice_sum<F>(a0.x + a0.y);
                     const float D1s = slice_sum<F>(a1.x + a1.y);
@@ -508,7 +520,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
                 bv[u] = ok ? __ldg(b + c0 + u) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) ps += abs_pow(av[u] - bv[u], q.pg);     // |0|^p = 0 for the padding
+            for (int u = 0; u < 8; ++u) ps += (P == kSim) ? -av[u] * bv[u] : abs_pow(av[u] - bv[u], q.pg);   // 0 for the padding
         }
         const float xp = -ps * q.coef;
         float M = q.include_pos ? xp : -INFINITY;
@@ -735,8 +747,8 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
                 float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int c = 0; c < DP; ++c) {
-                    a0 = Lp<P>::accum(__fadd2_rn(bb[c], na[r][c]), a0, q.pg);
-                    a1 = Lp<P>::accum(__fadd2_rn(bb[DP + c], na[r][c]), a1, q.pg);
+                    a0 = Lp<P>::pair_acc(bb[c], na[r][c], a0, q.pg);
+                    a1 = Lp<P>::pair_acc(bb[DP + c], na[r][c], a1, q.pg);
                 }
                 float w0, w1;
                 const float D0 = slice_sum<F>(a0.x + a0.y), D1 = slice_sum<F>(a1.x + a1.y);
@@ -750,8 +762,8 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
                 }
 #pragma unroll
                 for (int c = 0; c < DP; ++c) {
-                    gacc[r][c] = Lp<P>::grad(w0, __fadd2_rn(bb[c], na[r][c]), gacc[r][c], q.pg);
-                    gacc[r][c] = Lp<P>::grad(w1, __fadd2_rn(bb[DP + c], na[r][c]), gacc[r][c], q.pg);
+                    gacc[r][c] = Lp<P>::pair_grad(w0, bb[c], na[r][c], gacc[r][c], q.pg);
+                    gacc[r][c] = Lp<P>::pair_grad(w1, bb[DP + c], na[r][c], gacc[r][c], q.pg);
                 }
             }
         }
@@ -818,7 +830,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         cp_s[tid] = cpv;
     }
     __syncthreads();
-    const float scale = q.pg * (ro.scale_by_E ? E_u : 1.f);
+    const float scale = (P == kSim ? 1.f : q.pg) * (ro.scale_by_E ? E_u : 1.f);
     const int nel = ROWS * q.d;
     for (int idx = tid; idx < nel; idx += kThreads) {
         const int r = idx / q.d, c = idx - r * q.d;
@@ -835,9 +847,15 @@ __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) 
         }
         float g = scale * acc;
         if (ro.with_pos) {
-            const float gp = cp_s[r] * dabs_pow(__ldg(ro.O + (size_t)row * ro.ldO + c) - __ldg(ro.Z2 + (size_t)row * ro.ld2 + c), q.pg);
-            g += gp;
-            if (ro.g_z2) ro.g_z2[(size_t)row * ro.ldg2 + c] = -gp;
+            const float ov = __ldg(ro.O + (size_t)row * ro.ldO + c), zv = __ldg(ro.Z2 + (size_t)row * ro.ld2 + c);
+            if constexpr (P == kSim) {     // pos-"distance" -o.z2: d/do = -z2, d/dz2 = -o
+                g -= cp_s[r] * zv;
+                if (ro.g_z2) ro.g_z2[(size_t)row * ro.ldg2 + c] = -cp_s[r] * ov;
+            } else {
+                const float gp = cp_s[r] * dabs_pow(ov - zv, q.pg);
+                g += gp;
+                if (ro.g_z2) ro.g_z2[(size_t)row * ro.ldg2 + c] = -gp;
+            }
         }
         if (ro.g_out) ro.g_out[(size_t)row * ro.ldg + c] = g;
     }
@@ -937,18 +955,20 @@ int occ_bwd_pd() {
 
 #endif  // __CUDACC__
 
-// one translation unit per exponent keeps the build parallel: lpnce_p{0,1,2,3,4}.cu define these
+// one translation unit per exponent keeps the build parallel: lpnce_p{0,1,2,3,4,5}.cu define these (5 = kSim)
 int launch_fwd_p0(int DP, int F, const FwdParams& q, dim3 g, cudaStream_t s, int r4);
 int launch_fwd_p1(int DP, int F, const FwdParams& q, dim3 g, cudaStream_t s, int r4);
 int launch_fwd_p2(int DP, int F, const FwdParams& q, dim3 g, cudaStream_t s, int r4);
 int launch_fwd_p3(int DP, int F, const FwdParams& q, dim3 g, cudaStream_t s, int r4);
 int launch_fwd_p4(int DP, int F, const FwdParams& q, dim3 g, cudaStream_t s, int r4);
+int launch_fwd_p5(int DP, int F, const FwdParams& q, dim3 g, cudaStream_t s, int r4);
 int launch_bwd_p0(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p1(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p2(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p3(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
 int launch_bwd_p4(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
-int occ_fwd_p0(int DP, int F, int r4); int occ_fwd_p1(int DP, int F, int r4); int occ_fwd_p2(int DP, int F, int r4); int occ_fwd_p3(int DP, int F, int r4); int occ_fwd_p4(int DP, int F, int r4);
-int occ_bwd_p0(int DP, int F); int occ_bwd_p1(int DP, int F); int occ_bwd_p2(int DP, int F); int occ_bwd_p3(int DP, int F); int occ_bwd_p4(int DP, int F);
+int launch_bwd_p5(int DP, int F, const BwdParams& q, dim3 g, cudaStream_t s);
+int occ_fwd_p0(int DP, int F, int r4); int occ_fwd_p1(int DP, int F, int r4); int occ_fwd_p2(int DP, int F, int r4); int occ_fwd_p3(int DP, int F, int r4); int occ_fwd_p4(int DP, int F, int r4); int occ_fwd_p5(int DP, int F, int r4);
+int occ_bwd_p0(int DP, int F); int occ_bwd_p1(int DP, int F); int occ_bwd_p2(int DP, int F); int occ_bwd_p3(int DP, int F); int occ_bwd_p4(int DP, int F); int occ_bwd_p5(int DP, int F);
 
 }  // namespace clica

@@ -7,7 +7,9 @@ of the reference on ``sys.path`` that import resolves here:
 * :class:`LpSimCLRLoss` keeps the reference constructor and call signature (``losses.py:416-431``) and
   return structure ``(mean, per_item, [pos_mean, neg_mean])`` (``losses.py:467-477``); for CUDA fp32
   inputs with ``p >= 1`` and ``pow=True`` it runs the fused CUDA kernel (forward and backward).
-* every other name of the reference module (SimCLRLoss, CLLoss, ...) is re-exported from the reference
+* :class:`SimCLRLoss` (``losses.py:162-202``, selected by ``main_mlp.py:146-147`` for ``--p 0``) runs the same
+  fused kernels in their dot-product-similarity form (logit = z1.z3 / tau) for CUDA fp32 inputs.
+* every other name of the reference module (CLLoss, UniformityLoss, ...) is re-exported from the reference
   checkout when one is reachable -- none of them is on the hot path.
 * inputs outside the kernel's domain (CPU tensors = BASELINE config 1 "reference plumbing", p < 1,
   pow=False, non-fp32, d > 320) are handed to the reference's own ``LpSimCLRLoss.loss`` -- explicitly, with
@@ -41,6 +43,63 @@ else:
 _MAX_D = 320
 _warned = set()
 
+if _ref is not None:
+    _SimBase = _ref.SimCLRLoss
+else:
+    class _SimBase:   # stand-in with the reference constructor (losses.py:172-175)
+        def __init__(self, normalize=False, tau=1.0, alpha=0.5):
+            self.normalize, self.tau, self.alpha = normalize, tau, alpha
+
+        def __call__(self, z1, z2_con_z1, z3, z1_rec, z2_con_z1_rec, z3_rec):
+            return self.loss(z1, z2_con_z1, z3, z1_rec, z2_con_z1_rec, z3_rec)
+
+
+def _cuda_domain(tensors, max_d=_MAX_D):
+    for t in tensors:
+        if not isinstance(t, torch.Tensor):
+            return "non-tensor input"
+        if not t.is_cuda:
+            return "CPU tensors"
+        if t.dtype != torch.float32:
+            return f"dtype {t.dtype}"
+        if t.dim() != 2:
+            return f"{t.dim()}-D input"
+    if tensors[0].shape[1] > max_d:
+        return f"feature width {tensors[0].shape[1]} > {max_d}"
+    return None
+
+
+def _delegate(cls_name, why, call):
+    if _ref is None:
+        raise RuntimeError(f"{cls_name}: {why} is outside the CUDA kernel's domain and no reference "
+                           "checkout is reachable (set CLICA_REFERENCE_DIR)")
+    if (cls_name, why) not in _warned:
+        _warned.add((cls_name, why))
+        warnings.warn(f"clica_b200.{cls_name}: {why} -> delegating to the reference's torch code", stacklevel=3)
+    return call()
+
+
+class SimCLRLoss(_SimBase):
+    """InfoNCE on dot-product similarities (reference ``losses.py:162-202``), fused on sm_100a.
+
+    Args (identical to the reference): normalize=False, tau=1.0, alpha=0.5.  ``normalize=True`` divides the three
+    inputs by their row norms with torch ops (O(B*d), autograd chains through) before the fused kernel."""
+
+    def loss(self, z1, z2_con_z1, z3, z1_rec, z2_con_z1_rec, z3_rec):
+        del z1, z2_con_z1, z3
+        why = _cuda_domain((z1_rec, z2_con_z1_rec, z3_rec))
+        if why is not None:
+            return _delegate("SimCLRLoss", why,
+                             lambda: super(SimCLRLoss, self).loss(None, None, None, z1_rec, z2_con_z1_rec, z3_rec))
+        if self.normalize:
+            z1_rec = z1_rec / torch.norm(z1_rec, p=2, dim=-1, keepdim=True)
+            z2_con_z1_rec = z2_con_z1_rec / torch.norm(z2_con_z1_rec, p=2, dim=-1, keepdim=True)
+            z3_rec = z3_rec / torch.norm(z3_rec, p=2, dim=-1, keepdim=True)
+        # p = 0 selects the dot-product form of the kernel family: "distance" -z1.z3, positive "distance" -z1.z2
+        mean, per_item, pos_mean, neg_mean = _F.lp_infonce(z1_rec, z2_con_z1_rec, z3_rec, 0.0, float(self.tau),
+                                                           float(self.alpha), True)
+        return mean, per_item, [pos_mean, neg_mean]
+
 
 class LpSimCLRLoss(_Base):
     """Extended InfoNCE objective on an Lp norm (reference ``losses.py:405-477``), fused on sm_100a.
@@ -70,14 +129,8 @@ class LpSimCLRLoss(_Base):
         del z1, z2_con_z1, z3           # unused by the reference as well (losses.py:431); may be None
         why = self._outside_domain(z1_rec, z2_con_z1_rec, z3_rec)
         if why is not None:
-            if _ref is None:
-                raise RuntimeError(f"LpSimCLRLoss: {why} is outside the CUDA kernel's domain and no reference "
-                                   "checkout is reachable (set CLICA_REFERENCE_DIR)")
-            if why not in _warned:
-                _warned.add(why)
-                warnings.warn(f"clica_b200.LpSimCLRLoss: {why} -> delegating to the reference's torch code",
-                              stacklevel=2)
-            return super().loss(None, None, None, z1_rec, z2_con_z1_rec, z3_rec)
+            return _delegate("LpSimCLRLoss", why,
+                             lambda: super(LpSimCLRLoss, self).loss(None, None, None, z1_rec, z2_con_z1_rec, z3_rec))
         mean, per_item, pos_mean, neg_mean = _F.lp_infonce(
             z1_rec, z2_con_z1_rec, z3_rec, float(self.p), float(self.tau), float(self.alpha),
             bool(self.simclr_compatibility_mode))

@@ -27,6 +27,8 @@ def main(argv=None):
     ap.add_argument("--reference", default=_default_reference(),
                     help="reference checkout (default: $CLICA_REFERENCE_DIR, /root/reference, then baseline/_ref)")
     ap.add_argument("--script", default="main_mlp.py")
+    ap.add_argument("--device-samplers", action="store_true",
+                    help="install clica_b200.samplers behind the reference's `spaces` module (one launch per draw, no host syncs)")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     args = ap.parse_args(argv)
     ref = os.path.abspath(args.reference)
@@ -36,6 +38,9 @@ def main(argv=None):
     import clica_b200
     os.environ["CLICA_REFERENCE_DIR"] = ref
     sys.path[:] = [clica_b200.DROPIN_DIR, ref] + [p for p in sys.path if p not in (clica_b200.DROPIN_DIR, ref)]
+    if args.device_samplers:
+        from clica_b200 import samplers
+        samplers.install()
     rest = args.script_args
     if rest and rest[0] == "--":
         rest = rest[1:]

@@ -247,6 +247,22 @@ CLICA_API int clica_mixing_fwd(const float* x, int ldx, const float* const* W, i
  * Families: 0 loss fwd, 1 loss bwd, 2 loss finalize/prep/reduce, 3 tcgen05 GEMM, 4 CUDA-core GEMM,
  *           5 Adam, 6 misc (column sums, operand packing).
  * ---------------------------------------------------------------------------------------------- */
+/* ------------------------------------------------------------------------------------------------
+ * Device-side latent samplers.   replaces, for CUDA devices, the host-side samplers of
+ *   spaces.py:47-119 (NRealSpace), :134-231 (NSphereSpace), :273-351 (NBoxSpace) and
+ *   spaces_utils.py:82-142 (generalized normal via CPU Gamma draws; rejection loops with a host sync per round)
+ * out[rows, n] (ld) <- rows samples;  space: 0 R^n, 1 unit sphere (draw in R^n, project), 2 box [box_lo, box_hi]
+ * (every element is redrawn until it lies in the box);  dist: 0 uniform (sphere, box), 1 normal(mean, scale),
+ * 2 laplace(mean, scale), 3 generalized normal(mean, scale, p) = mean + scale * sign * Gamma(1/p, 1)^(1/p).
+ * mean: NULL / one row (mean_rows = 1) / one row per sample (mean_rows = rows).  Same distributions as the
+ * reference, different random stream: Philox4x32-10 keyed by `seed`, every (element, attempt, offset) owns its
+ * counter, so a (seed, offset) pair names a reproducible draw; callers advance `offset` per call.  One launch,
+ * no host synchronisation.
+ * ---------------------------------------------------------------------------------------------- */
+CLICA_API int clica_sample_latents(float* out, int ld, int rows, int n, int space, int dist, const float* mean,
+                     int ld_mean, int mean_rows, float scale, float p, float box_lo, float box_hi,
+                     uint64_t seed, uint64_t offset, void* stream);
+
 /* The persistent tcgen05 GEMMs normally launch one CTA (or CTA pair) per SM.  clica_tc_set_sm_reserve(n) makes
  * every later GEMM launch of this process leave n SMs free (0 <= n <= 64; default 0) -- the multi-GPU step sets it
  * while NCCL's all-reduce of a finished gradient bucket runs concurrently with the remaining backward GEMMs.

@@ -16,6 +16,7 @@ Fixtures
                       values of every parameter (pins init scheme + RNG draw order) + fwd/bwd digests
   step_n5.npz         3 Adam steps of the main_mlp.py train_step body (n=5, B=64, p=2): per-step
                       losses and parameter digests
+  simclr_<name>.npz   losses.SimCLRLoss cases (losses.py:162-202; `--only simclr` regenerates just these)
 """
 import argparse
 import os
@@ -137,6 +138,65 @@ def make_loss_fixtures(losses):
         print("wrote lpnce_%s.npz  loss=%.6f" % (name, store["loss_mean_64"]))
 
 
+def simclr_cases():
+    rng = np.random.RandomState(20261018)
+
+    def pair(B, d, scale=1.0, c=0.05):
+        z1 = (rng.randn(B, d) * scale).astype(np.float32)
+        z2 = (z1 + c * rng.randn(B, d)).astype(np.float32)
+        return z1, z2
+
+    def unit(z):
+        return (z / np.linalg.norm(z, axis=1, keepdims=True)).astype(np.float32)
+
+    cases = {}
+    z1, z2 = pair(64, 10)
+    cases["roll_d10"] = dict(z1=unit(z1), z2=unit(z2), normalize=False, tau=1.0, alpha=0.5, roll=True)
+    z1, z2 = pair(50, 7)
+    cases["indep_normalize_tau05"] = dict(z1=z1, z2=z2, z3=rng.randn(77, 7).astype(np.float32), normalize=True,
+                                          tau=0.5, alpha=0.5, roll=False)
+    z1, z2 = pair(40, 16, scale=3.0)
+    cases["indep_large_logits"] = dict(z1=z1, z2=z2, z3=(rng.randn(61, 16) * 3).astype(np.float32), normalize=False,
+                                       tau=0.1, alpha=0.5, roll=False)
+    z1, z2 = pair(48, 10)
+    cases["roll_alpha03_weighted"] = dict(z1=unit(z1), z2=unit(z2), normalize=False, tau=0.7, alpha=0.3, roll=True,
+                                          gl=(rng.rand(48) - 0.3).astype(np.float32))
+    z1, z2 = pair(131, 40, scale=0.4)
+    cases["indep_d40_ragged"] = dict(z1=z1, z2=z2, z3=(rng.randn(259, 40) * 0.4).astype(np.float32), normalize=False,
+                                     tau=1.0, alpha=0.5, roll=False)
+    z1, z2 = pair(36, 128, scale=0.2)
+    cases["roll_d128_wide"] = dict(z1=z1, z2=z2, normalize=False, tau=1.0, alpha=0.5, roll=True)
+    return cases
+
+
+def make_simclr_fixtures(losses):
+    for name, c in simclr_cases().items():
+        store = dict(z1=c["z1"], z2=c["z2"], normalize=int(c["normalize"]), tau=c["tau"], alpha=c["alpha"],
+                     roll=int(c["roll"]))
+        if not c["roll"]:
+            store["z3"] = c["z3"]
+        if "gl" in c:
+            store["gl"] = c["gl"]
+        for tag, dt in (("64", torch.float64), ("32", torch.float32)):
+            a = _t(c["z1"], dt).requires_grad_(True)
+            b = _t(c["z2"], dt).requires_grad_(True)
+            n = torch.roll(a, 1, 0) if c["roll"] else _t(c["z3"], dt).requires_grad_(True)
+            crit = losses.SimCLRLoss(normalize=c["normalize"], tau=c["tau"], alpha=c["alpha"])
+            mean, per_item, parts = crit(None, None, None, a, b, n)
+            if "gl" in c:
+                (per_item * _t(c["gl"], dt)).sum().backward()
+            else:
+                mean.backward()
+            out = dict(loss_mean=mean.item(), loss_i=per_item.detach().numpy(), pos_mean=parts[0].item(),
+                       neg_mean=parts[1].item(), g1=a.grad.numpy(), g2=b.grad.numpy())
+            if not c["roll"]:
+                out["g3"] = n.grad.numpy()
+            for k, v in out.items():
+                store[f"{k}_{tag}"] = np.asarray(v)
+        np.savez_compressed(os.path.join(HERE, f"simclr_{name}.npz"), **store)
+        print("wrote simclr_%s.npz  loss=%.6f" % (name, store["loss_mean_64"]))
+
+
 def digest(t):
     a = t.detach().double().numpy().ravel()
     return np.array([a.sum(), np.abs(a).sum(), (a * a).sum()])
@@ -245,6 +305,7 @@ def make_step_fixture(losses, encoders):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--only", default=None, choices=[None, "simclr"])
     args = ap.parse_args()
     warnings.simplefilter("ignore", SyntaxWarning)
     sys.path.insert(0, args.reference)
@@ -252,7 +313,11 @@ def main():
     import encoders    # the reference's, unmodified
     assert os.path.dirname(os.path.abspath(losses.__file__)) == os.path.abspath(args.reference)
     torch.set_num_threads(1)   # deterministic summation order for the fp32 variants
+    if args.only == "simclr":
+        make_simclr_fixtures(losses)
+        return
     make_loss_fixtures(losses)
+    make_simclr_fixtures(losses)
     make_mlp_fixtures(encoders)
     make_step_fixture(losses, encoders)
 

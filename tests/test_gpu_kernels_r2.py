@@ -102,6 +102,7 @@ def test_p2_dot_form_against_the_oracle_and_the_subtract_form(kind, B, M, d, r4,
     tau = 0.8
     monkeypatch.setenv("CLICA_LPNCE_R4", r4)
     monkeypatch.setenv("CLICA_LPNCE_DOT", "1")
+    monkeypatch.setenv("CLICA_LPNCE_DOT_BWD", "1")        # the backward's dot form is opt-in (slower on B200): test it too
     dot = _loss_run(z1, z2, z3, 2.0, tau, True, cuda_device, False)
     monkeypatch.setenv("CLICA_LPNCE_DOT", "0")
     sub = _loss_run(z1, z2, z3, 2.0, tau, True, cuda_device, False)
@@ -124,6 +125,7 @@ def test_p2_dot_form_rolled_negatives_full_size(kind, cuda_device, monkeypatch):
     rng = np.random.RandomState(7)
     z1, z2, _ = _data(kind, B, B, d, rng)
     monkeypatch.setenv("CLICA_LPNCE_DOT", "1")
+    monkeypatch.setenv("CLICA_LPNCE_DOT_BWD", "1")
     dot = _loss_run(z1, z2, None, 2.0, tau, True, cuda_device, True)
     monkeypatch.setenv("CLICA_LPNCE_DOT", "0")
     sub = _loss_run(z1, z2, None, 2.0, tau, True, cuda_device, True)
@@ -172,3 +174,93 @@ def test_fused_weight_packing_is_bit_identical(cuda_device, monkeypatch):
         outs.append(F._lib.load().clica_launch_count(6) - launches0)
     assert torch.equal(outs[0], outs[2])
     assert outs[1] == 5 and outs[3] == 1          # five split launches -> one
+
+
+# ---- SimCLRLoss (losses.py:162-202): the kernel family in its dot-product-similarity form ----------------------
+def _simclr_cases():
+    import glob
+    from conftest import GOLDEN_DIR
+    return sorted(os.path.basename(p)[len("simclr_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "simclr_*.npz")))
+
+
+@pytest.mark.parametrize("name", _simclr_cases())
+def test_simclr_loss_on_the_golden_vectors_from_the_reference(name, cuda_device):
+    import sys
+    import clica_b200
+    from conftest import load_golden
+    sys.path.insert(0, clica_b200.DROPIN_DIR)
+    import losses
+    g = load_golden("simclr_" + name)
+    roll = bool(g["roll"])
+    a = torch.tensor(g["z1"], device=cuda_device, requires_grad=True)
+    b = torch.tensor(g["z2"], device=cuda_device, requires_grad=True)
+    n = torch.roll(a, 1, 0) if roll else torch.tensor(g["z3"], device=cuda_device, requires_grad=True)
+    crit = losses.SimCLRLoss(normalize=bool(g["normalize"]), tau=float(g["tau"]), alpha=float(g["alpha"]))
+    mean, per_item, parts = crit(None, None, None, a, b, n)
+    if "gl" in g:
+        (per_item * torch.tensor(g["gl"], device=cuda_device)).sum().backward()
+    else:
+        mean.backward()
+    # tolerance: the reference's own fp32 run defines the achievable band (logits of +-1e3 in `indep_large_logits`
+    # carry 1e-4 of absolute fp32 rounding); held to max(3x that, the Lp kernels' 5e-6 / 2e-5)
+    scale = max(1.0, float(np.abs(g["loss_i_64"]).max()))
+    ref_err = float(np.abs(g["loss_i_32"] - g["loss_i_64"]).max())
+    assert np.abs(per_item.detach().cpu().numpy() - g["loss_i_64"]).max() <= max(5e-6 * scale, 3 * ref_err)
+    assert abs(mean.item() - float(g["loss_mean_64"])) <= max(5e-6 * scale, 3 * ref_err)
+    assert abs(parts[0].item() - float(g["pos_mean_64"])) <= 5e-6 * max(1.0, abs(float(g["pos_mean_64"])))
+    assert abs(parts[1].item() - float(g["neg_mean_64"])) <= max(5e-6 * scale, 3 * ref_err)
+    term = float(np.abs(g["z1"]).max()) / (len(g["z1"]) * float(g["tau"]))
+    gmax = max(float(np.abs(g["g1_64"]).max()), 1e-30)
+    gtol = max(2e-5 * gmax, 3 * float(np.abs(g["g1_32"] - g["g1_64"]).max()), 2e-6 * term)
+    assert np.abs(a.grad.cpu().numpy() - g["g1_64"]).max() <= gtol
+    assert np.abs(b.grad.cpu().numpy() - g["g2_64"]).max() <= gtol
+    if not roll:
+        assert np.abs(n.grad.cpu().numpy() - g["g3_64"]).max() <= gtol
+
+
+@pytest.mark.parametrize("B,M,d,tau", [(300, 517, 10, 1.0), (257, 1031, 40, 0.5), (6144, 6144, 10, 1.0), (130, 257, 128, 2.0)])
+def test_simclr_random_shapes_against_the_oracle(B, M, d, tau, cuda_device):
+    from clica_b200 import functional as F
+    from oracle import simclr_oracle
+    rng = np.random.RandomState(B + d)
+    z1 = rng.randn(B, d).astype(np.float32)
+    z1 /= np.linalg.norm(z1, axis=1, keepdims=True)
+    z2 = (z1 + 0.05 * rng.randn(B, d)).astype(np.float32)
+    z3 = rng.randn(M, d).astype(np.float32)
+    z3 /= np.linalg.norm(z3, axis=1, keepdims=True)
+    a = torch.tensor(z1, device=cuda_device, requires_grad=True)
+    b = torch.tensor(z2, device=cuda_device, requires_grad=True)
+    n = torch.tensor(z3, device=cuda_device, requires_grad=True)
+    mean, per_item, pos_mean, neg_mean = F.lp_infonce(a, b, n, 0.0, tau, 0.5, True)
+    mean.backward()
+    rows = np.arange(0, B, max(1, B // 300))
+    ref = simclr_oracle.simclr(z1, z2, z3, tau, 0.5)
+    scale = max(1.0, float(np.abs(ref["loss_i"]).max()))
+    assert np.abs(per_item.detach().cpu().numpy()[rows] - ref["loss_i"][rows]).max() <= 5e-6 * scale
+    assert abs(mean.item() - ref["loss_mean"]) <= 5e-6 * scale
+    gmax = float(np.abs(ref["g1"]).max())
+    assert np.abs(a.grad.cpu().numpy() - ref["g1"]).max() <= 2e-5 * gmax
+    assert np.abs(b.grad.cpu().numpy() - ref["g2"]).max() <= 2e-5 * gmax
+    assert np.abs(n.grad.cpu().numpy() - ref["g3"]).max() <= 2e-5 * gmax
+
+
+def test_p_below_one_runs_through_the_reference_delegation_on_cuda(cuda_device):
+    """losses.py:433-442 (p < 1, unreachable from the CLIs): handed to the reference's own torch code on CUDA tensors --
+    needs baseline/_ref on the box (placed by build())."""
+    import sys
+    import warnings
+    import clica_b200
+    from clica_b200 import vendor
+    if vendor.vendored_dir() is None:
+        pytest.skip("baseline/_ref is absent")
+    sys.path.insert(0, clica_b200.DROPIN_DIR)
+    import losses
+    rng = np.random.RandomState(2)
+    a = torch.tensor(rng.randn(64, 6).astype(np.float32), device=cuda_device, requires_grad=True)
+    b = (a.detach() + 0.05).requires_grad_(True)
+    crit = losses.LpSimCLRLoss(p=0.5, tau=1.0, simclr_compatibility_mode=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean, per_item, parts = crit(None, None, None, a, b, torch.roll(a, 1, 0))
+    mean.backward()
+    assert torch.isfinite(mean) and per_item.shape == (64,) and torch.isfinite(a.grad).all()

@@ -1,0 +1,126 @@
+"""GPU (-m gpu): device-side latent samplers (clica_sample_latents behind the reference's `spaces` surface) --
+distribution checks against analytic CDFs (Kolmogorov-Smirnov, scipy) and, when baseline/_ref is present, two-sample KS
+against the reference's own host samplers (/root/reference/spaces.py:47-351, spaces_utils.py:82-142).
+Seeds are fixed, so the p-values are reproducible; acceptance p > 1e-3 per check with 20 000 samples."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+N = 20000
+PMIN = 1e-3
+
+
+@pytest.fixture(scope="module")
+def S(cuda_device):
+    import clica_b200
+    from clica_b200 import samplers, vendor
+    ref = vendor.vendored_dir()
+    if ref is None:
+        pytest.skip("baseline/_ref is absent (the samplers subclass the reference's space classes)")
+    if ref not in sys.path:
+        sys.path.append(ref)
+    import importlib
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)
+        ref_spaces = importlib.import_module("spaces")
+    if getattr(ref_spaces, "__clica_device_samplers__", False):
+        mod = ref_spaces
+    else:
+        mod = samplers.build_module(ref_spaces)
+    torch.manual_seed(0)
+    return mod, ref_spaces
+
+
+def _ks(x, cdf):
+    from scipy import stats
+    return stats.kstest(np.asarray(x, dtype=np.float64), cdf).pvalue
+
+
+def _ks2(x, y):
+    from scipy import stats
+    return stats.ks_2samp(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)).pvalue
+
+
+def test_sphere_uniform_and_projected_normal(S, cuda_device):
+    from scipy import stats
+    mod, ref = S
+    n = 10
+    sp = mod.NSphereSpace(n)
+    z = sp.uniform(N, device=cuda_device)
+    assert z.is_cuda and z.shape == (N, n)
+    assert (z.norm(dim=-1) - 1).abs().max().item() < 1e-5
+    zc = z.cpu().numpy()
+    for c in (0, 4, 9):       # a coordinate of a uniform point on S^{n-1}: (x + 1) / 2 ~ Beta((n-1)/2, (n-1)/2)
+        assert _ks((zc[:, c] + 1) / 2, stats.beta((n - 1) / 2, (n - 1) / 2).cdf) > PMIN
+    assert np.abs(np.corrcoef(zc.T) - np.eye(n)).max() < 0.04
+    # conditional: project(mean + 0.05 N(0, I)); cosine to the mean and a coordinate, against the reference's sampler
+    zt = sp.normal(z, 0.05, N, device=cuda_device)
+    assert (zt.norm(dim=-1) - 1).abs().max().item() < 1e-5
+    torch.manual_seed(1)
+    zt_ref = ref.NSphereSpace(n).normal(z.cpu(), 0.05, N, device="cpu")
+    cos, cos_ref = (zt * z).sum(-1).cpu().numpy(), (zt_ref * z.cpu()).sum(-1).numpy()
+    assert _ks2(cos, cos_ref) > PMIN
+    assert _ks2((zt - z)[:, 3].cpu().numpy(), (zt_ref - z.cpu())[:, 3].numpy()) > PMIN
+
+
+@pytest.mark.parametrize("p", [1.5, 3.0, 4.0])
+def test_real_space_normal_laplace_generalized_normal(S, cuda_device, p):
+    from scipy import stats
+    mod, ref = S
+    n = 6
+    sp = mod.NRealSpace(n)
+    mean = torch.linspace(-1, 1, n)
+    x = sp.normal(mean, 0.7, N, device=cuda_device).cpu().numpy()
+    assert _ks((x[:, 2] - mean[2].item()) / 0.7, stats.norm.cdf) > PMIN
+    x = sp.laplace(mean, 0.3, N, device=cuda_device).cpu().numpy()
+    assert _ks(x[:, 5] - mean[5].item(), stats.laplace(scale=0.3).cdf) > PMIN
+    x = sp.generalized_normal(mean, 0.5, p, N, device=cuda_device).cpu().numpy()
+    # mean + lbd * sign * Gamma(1/p)^(1/p)  ==  generalized normal with shape p and scale lbd
+    assert _ks(x[:, 1] - mean[1].item(), stats.gennorm(beta=p, scale=0.5).cdf) > PMIN
+    torch.manual_seed(2)
+    x_ref = ref.NRealSpace(n).generalized_normal(mean, 0.5, p, N, device="cpu").numpy()
+    assert _ks2(x[:, 4], x_ref[:, 4]) > PMIN
+
+
+def test_box_uniform_and_truncated_conditionals(S, cuda_device):
+    from scipy import stats
+    mod, ref = S
+    n = 5
+    sp = mod.NBoxSpace(n, -1.0, 1.0)
+    u = sp.uniform(N, device=cuda_device)
+    assert u.min().item() >= -1 and u.max().item() <= 1
+    assert _ks(u[:, 0].cpu().numpy(), stats.uniform(-1, 2).cdf) > PMIN
+    mean = torch.tensor([0.0, 0.9, -0.95, 0.5, -0.2])
+    x = sp.normal(mean, 0.3, N, device=cuda_device)
+    assert x.min().item() >= -1 and x.max().item() <= 1
+    xc = x.cpu().numpy()
+    for c in (1, 2, 3):       # per-element rejection == truncated normal per coordinate
+        a, b = (-1 - mean[c].item()) / 0.3, (1 - mean[c].item()) / 0.3
+        assert _ks(xc[:, c], stats.truncnorm(a, b, loc=mean[c].item(), scale=0.3).cdf) > PMIN
+    torch.manual_seed(3)
+    xl = sp.laplace(mean, 0.4, N, device=cuda_device).cpu().numpy()
+    xl_ref = ref.NBoxSpace(n, -1.0, 1.0).laplace(mean, 0.4, N, device="cpu").numpy()
+    assert np.abs(xl).max() <= 1 and _ks2(xl[:, 1], xl_ref[:, 1]) > PMIN
+    xg = sp.generalized_normal(mean, 0.4, 3, N, device=cuda_device).cpu().numpy()
+    xg_ref = ref.NBoxSpace(n, -1.0, 1.0).generalized_normal(mean, 0.4, 3, N, device="cpu").numpy()
+    assert np.abs(xg).max() <= 1 and _ks2(xg[:, 2], xg_ref[:, 2]) > PMIN
+
+
+def test_draws_are_reproducible_and_calls_are_independent(S, cuda_device):
+    from clica_b200 import samplers
+    mod, _ = S
+    import itertools
+    sp = mod.NSphereSpace(10)
+    torch.manual_seed(123)
+    samplers._calls = itertools.count(1)
+    a1, a2 = sp.uniform(256, device=cuda_device), sp.uniform(256, device=cuda_device)
+    torch.manual_seed(123)
+    samplers._calls = itertools.count(1)
+    b1 = sp.uniform(256, device=cuda_device)
+    assert torch.equal(a1, b1) and not torch.equal(a1, a2)
+    # CPU devices keep the reference's own sampler
+    assert not sp.uniform(4, device="cpu").is_cuda

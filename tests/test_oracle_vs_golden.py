@@ -128,3 +128,47 @@ def test_port_encoder_structure_and_init_match_reference():
         assert np.array_equal(v.numpy().ravel()[:8], g["head_" + k]), k
     y = f(torch.tensor(g["x"]))
     _close(y.detach().numpy(), g["y"], 1e-5, 1e-7, "y")
+
+
+def simclr_cases():
+    import glob
+    import os
+    from conftest import GOLDEN_DIR
+    return sorted(os.path.basename(p)[len("simclr_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "simclr_*.npz")))
+
+
+@pytest.mark.parametrize("name", simclr_cases())
+def test_simclr_oracle_matches_reference_fp64(name):
+    """oracle/simclr_oracle.py vs losses.SimCLRLoss of the reference (fp64 run), incl. normalize=True via the chain rule."""
+    from oracle import simclr_oracle
+    g = load_golden("simclr_" + name)
+    roll, normalize = bool(g["roll"]), bool(g["normalize"])
+    z1, z2 = g["z1"].astype(np.float64), g["z2"].astype(np.float64)
+    z3 = np.roll(z1, 1, axis=0) if roll else g["z3"].astype(np.float64)
+
+    def unit(z):
+        return z / np.linalg.norm(z, axis=1, keepdims=True)
+
+    def unit_vjp(z, gu):      # gradient through z -> z / |z|
+        n = np.linalg.norm(z, axis=1, keepdims=True)
+        u = z / n
+        return (gu - u * (u * gu).sum(1, keepdims=True)) / n
+    a, b, c = (unit(z1), unit(z2), unit(z3)) if normalize else (z1, z2, z3)
+    out = simclr_oracle.simclr(a, b, c, float(g["tau"]), float(g["alpha"]), gl=g["gl"] if "gl" in g else None)
+    g1, g2, g3 = out["g1"], out["g2"], out["g3"]
+    if normalize:
+        g1, g2, g3 = unit_vjp(z1, g1), unit_vjp(z2, g2), unit_vjp(z3, g3)
+    if roll:
+        g1 = g1 + np.roll(g3, -1, axis=0)
+    scale = max(1.0, float(np.abs(g["loss_i_64"]).max()))
+    _close(out["loss_i"], g["loss_i_64"], 0, 1e-10 * scale, "loss_i")
+    _close(out["loss_mean"], g["loss_mean_64"], 0, 1e-10 * scale, "loss_mean")
+    _close(out["pos_mean"], g["pos_mean_64"], 1e-12, 1e-10 * scale, "pos_mean")
+    _close(out["neg_mean"], g["neg_mean_64"], 1e-12, 1e-10 * scale, "neg_mean")
+    # gradients are differences of terms of size |z| / (B tau); when a row's positive takes all the soft-max mass they
+    # cancel almost completely (case indep_large_logits), so the absolute tolerance is relative to the TERM size
+    gmax = max(np.abs(g["g1_64"]).max(), np.abs(z1).max() / (len(z1) * float(g["tau"])))
+    _close(g1, g["g1_64"], 1e-9, 1e-11 * gmax, "g1")
+    _close(g2, g["g2_64"], 1e-9, 1e-11 * gmax, "g2")
+    if not roll:
+        _close(g3, g["g3_64"], 1e-9, 1e-11 * gmax, "g3")
