@@ -18,6 +18,7 @@ exactly those semantics -- every anchor sees ALL negatives of the global batch -
 The kernels are reached through ``ops`` (default: the CUDA C-ABI); tests inject an oracle-backed ``ops`` to
 exercise this host logic on CPU with the gloo backend.
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -154,11 +155,18 @@ class overlapped_grad_allreduce:
         self.sync = F.grad_sync(lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
 
     def __enter__(self):
+        # SMs the persistent tcgen05 GEMMs of the backward leave free for NCCL's reduction kernels, which otherwise only
+        # get an SM when a GEMM CTA retires (CLICA_ALLREDUCE_SM_RESERVE, default 0: measured in profiles/r2_scaling.md)
+        self.reserve = int(os.environ.get("CLICA_ALLREDUCE_SM_RESERVE", "0"))
+        if self.reserve > 0:
+            _lib.check(_lib.load().clica_tc_set_sm_reserve(self.reserve), "clica_tc_set_sm_reserve")
         self.sync.__enter__()
         return self
 
     def __exit__(self, exc_type, exc, tb):
         self.sync.__exit__(exc_type, exc, tb)
+        if self.reserve > 0:
+            _lib.load().clica_tc_set_sm_reserve(0)
         if exc_type is None:
             rest = [p for p in self.params if id(p) not in self.sync.covered]
             allreduce_grads(rest, self.group)

@@ -25,10 +25,18 @@ for (n, B, p) in [(10, 2048, 2), (5, 1024, 1), (40, 1024, 3)]:
     sl = slice(rank * Bl, (rank + 1) * Bl)
     a, b = f(g(z1[sl])), f(g(z2[sl]))
     loss, _, parts = sharded.sharded_lp_infonce(a, b, p, 1.0, 0.5, True)
-    loss.backward()
+    loss.backward(retain_graph=True)
     sharded.allreduce_grads(list(f.parameters()))
     g_sh = [prm.grad.clone() for prm in f.parameters()]
     f.zero_grad()
+    # same backward with the bucketed all-reduce issued from inside the encoder backward (overlapped with its GEMMs)
+    with sharded.overlapped_grad_allreduce(f.parameters()):
+        loss.backward()
+    g_ov = [prm.grad.clone() for prm in f.parameters()]
+    f.zero_grad()
+    gm = max(t.abs().max().item() for t in g_sh)
+    err_ov = max((x - y).abs().max().item() for x, y in zip(g_sh, g_ov)) / gm
+    assert err_ov <= 1e-6, err_ov
     crit = losses.LpSimCLRLoss(p=p, tau=1.0, simclr_compatibility_mode=True)
     a2, b2 = f(g(z1)), f(g(z2))
     tot, _, parts2 = crit(None, None, None, a2, b2, torch.roll(a2, 1, 0))
@@ -36,7 +44,7 @@ for (n, B, p) in [(10, 2048, 2), (5, 1024, 1), (40, 1024, 3)]:
     gmax = max(prm.grad.abs().max().item() for prm in f.parameters())
     err = max((gs - prm.grad).abs().max().item() for gs, prm in zip(g_sh, f.parameters())) / gmax
     if rank == 0:
-        print(f"n={n} B={B} p={p} world={world}: loss sharded {loss.item():.7f} single {tot.item():.7f}  max grad err / max grad = {err:.2e}", flush=True)
+        print(f"n={n} B={B} p={p} world={world}: loss sharded {loss.item():.7f} single {tot.item():.7f}  max grad err / max grad = {err:.2e}  (overlapped vs flat all-reduce: {err_ov:.1e})", flush=True)
     assert abs(loss.item() - tot.item()) <= 5e-6 * max(1.0, abs(tot.item())) and err <= 5e-4, (loss.item(), tot.item(), err)
 # the CUDA-graph sharded step (NCCL collectives recorded into the graph) follows the eager sharded trajectory
 if os.environ.get("CLICA_CHECK_GRAPH", "1") != "0":
