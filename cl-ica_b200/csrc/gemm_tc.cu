@@ -30,7 +30,8 @@ namespace clica {
 namespace {
 
 constexpr int BM = 128, BK = 32;                       // BK fp32 = 128 bytes = one swizzle span; BN = 128 or 256 (template)
-constexpr int kTcThreads = 320;                          // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kConvWarps = 4;                            // operand-converter warps (in-kernel hi/lo split)
+constexpr int kTcThreads = 320 + 32 * kConvWarps;        // TMA warp + MMA warp + 8 epilogue warps + converter warps
 constexpr int kMaxStages = 8;
 constexpr int kPairDefault = 1;                          // CLICA_TC_PAIR default (1: CTA pairs, tcgen05 cta_group::2)
 constexpr size_t kEpiStageBytes = 8 * 4096;                 // one 32 x 32 fp32 staging block per epilogue warp
@@ -39,6 +40,7 @@ struct TcKernelParams {
     int Mo, No;
     int kb_total, kb_per_split, splits;
     int a_mn, b_mn, nterms, stages;
+    int conv_a, conv_b;               // 3xTF32 with a single stored fp32 plane: the converter warps split it in shared memory
     int epi;
     const float* bias; float slope;
     const float* aux; int ldaux;
@@ -71,6 +73,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// same, acquiring at cluster scope: the arrivals (and the shared-memory writes they publish) may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "WAIT_DONE_C:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -152,12 +166,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA of the pair
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar_cluster_addr) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(tm), "r"(bar_cluster_addr), "r"(x), "r"(y) : "memory");
-}
 // tcgen05.commit that arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -219,18 +227,13 @@ __device__ __forceinline__ int tile_width(int rem) {
     return w < BN ? w : BN;
 }
 
-template <int ROWS, int CTAS>
-__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar,
-                                             uint32_t bar_cluster) {
+template <int ROWS>
+__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar) {
     if (!mn_major) {
-        if constexpr (CTAS == 1) tma_load_2d(dst, tm, k0, mn0, bar);
-        else tma_load_2d_pair(dst, tm, k0, mn0, bar_cluster);
+        tma_load_2d(dst, tm, k0, mn0, bar);
     } else {
 #pragma unroll
-        for (int j = 0; j < ROWS / 32; ++j) {
-            if constexpr (CTAS == 1) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
-            else tma_load_2d_pair(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar_cluster);
-        }
+        for (int j = 0; j < ROWS / 32; ++j) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
     }
 }
 
@@ -252,7 +255,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                const TcKernelParams q) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];     // this CTA's TMA bytes of the stage have landed
+    __shared__ __align__(8) uint64_t ready_bar[kMaxStages];    // (leader CTA) the stage is converted in BOTH CTAs: MMA may read
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
@@ -273,10 +277,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (tm && threadIdx.x == 0) tm[0] = clock64();
 
     if (warp == 0 && lane == 0) {
-        // pair mode: the leader's full barrier expects the TMA bytes of BOTH CTAs (one arrive.expect_tx by the leader's
-        // producer; the peer's loads complete_tx on it); the leader's accumulator-free barrier takes the 8 epilogue
-        // warps of each CTA
-        for (int s = 0; s < q.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // every CTA's loads complete on its OWN full barrier; its converter warps wait there, split the fp32 planes
+        // that were stored un-split, and arrive (remotely, for the peer) on the LEADER's ready barrier, which the MMA
+        // warp waits on; the leader's accumulator-free barrier takes the 8 epilogue warps of each CTA
+        for (int s = 0; s < q.stages; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps * CTAS); mbar_init(&empty_bar[s], 1);
+        }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8 * CTAS); }
         fence_barrier_init();
     }
@@ -304,23 +310,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     const uint32_t s = it % (uint32_t)q.stages;
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    uint32_t fb = 0;                                 // pair mode: the LEADER's full barrier
-                    if constexpr (CTAS == 1) {
-                        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                    } else {
-                        // the peer's loads for this phase cannot start before its own empty barrier flipped, i.e. before
-                        // the leader's full barrier finished the previous phase: a complete_tx that overtakes this
-                        // expect_tx only drives the (signed) tx-count negative for a moment
-                        fb = mapa_u32(smem_u32(&full_bar[s]), 0u);
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes * CTAS);
-                    }
+                    const uint32_t a_planes = (nplanes == 2 && !q.conv_a) ? 2u : 1u, b_planes = (nplanes == 2 && !q.conv_b) ? 2u : 1u;
+                    mbar_arrive_expect_tx(&full_bar[s], a_planes * kABytes + b_planes * kBBytes);
                     const uint32_t sa = tiles + s * stage_bytes;
                     const uint32_t sb = sa + nplanes * kABytes;
                     const int k0 = kb * BK;
-                    load_operand<BM, CTAS>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s], fb);
-                    if (nplanes == 2) load_operand<BM, CTAS>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s], fb);
-                    load_operand<BNL, CTAS>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s], fb);
-                    if (nplanes == 2) load_operand<BNL, CTAS>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s], fb);
+                    load_operand<BM>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s]);
+                    if (a_planes == 2) load_operand<BM>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s]);
+                    load_operand<BNL>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s]);
+                    if (b_planes == 2) load_operand<BNL>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s]);
                     if (tm && it == 0) tm[2] = clock64();
                 }
             }
@@ -346,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)q.stages;
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
-                    mbar_wait(&full_bar[s], ph);
+                    if constexpr (CTAS == 1) mbar_wait(&ready_bar[s], ph); else mbar_wait_cluster(&ready_bar[s], ph);
                     tcgen05_fence_after();
                     if (tm && it == 0) tm[3] = clock64();
                     const uint32_t sa = tiles + s * stage_bytes;
@@ -373,6 +371,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 // accumulator complete (pair mode: each CTA's epilogue drains its own 128 TMEM lanes)
                 if constexpr (CTAS == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_pair(&tmem_full_bar[as]);
                 if (tm) tm[4] = clock64();
+            }
+        }
+    } else if (warp >= 10) {
+        // ===== operand converters: warps 10..13.  3xTF32 operands that live in HBM as ONE fp32 plane (activations and
+        // their gradients: half the DRAM / L2 bytes of a stored (hi, lo) pair) are split here, in shared memory, right
+        // after the TMA delivered them: hi = tf32-round(v) overwrites the tile in place, lo = tf32-round(v - hi) goes to
+        // the stage's lo slot at the same offset -- the layout (K-major / MN-major swizzle) is irrelevant to an
+        // element-wise pass, and the values are bit-identical to planes split by split_planes_kernel.
+        const int ctid = threadIdx.x - 320;
+        uint8_t* const tile_base = smem_raw + (tiles - smem_u32(smem_raw));
+        auto convert = [&](uint8_t* src, uint32_t bytes, uint32_t lo_off) {
+            for (uint32_t i = (uint32_t)ctid * 16u; i < bytes; i += (uint32_t)kConvWarps * 32u * 16u) {
+                const float4 v = *reinterpret_cast<const float4*>(src + i);
+                float4 h, l;
+                h.x = round_to_tf32(v.x); h.y = round_to_tf32(v.y); h.z = round_to_tf32(v.z); h.w = round_to_tf32(v.w);
+                l.x = round_to_tf32(v.x - h.x); l.y = round_to_tf32(v.y - h.y);
+                l.z = round_to_tf32(v.z - h.z); l.w = round_to_tf32(v.w - h.w);
+                *reinterpret_cast<float4*>(src + i) = h;
+                *reinterpret_cast<float4*>(src + i + lo_off) = l;
+            }
+        };
+        const uint32_t ready_addr = (CTAS == 2) ? mapa_u32(smem_u32(&ready_bar[0]), 0u) : 0u;
+        uint32_t it = 0;
+        for (int w = unit_id; w < total; w += num_units) {
+            const int rest = w / num_m;
+            const int kb0 = (rest / num_n) * q.kb_per_split;
+            const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const uint32_t s = it % (uint32_t)q.stages;
+                const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                if (nplanes == 2 && (q.conv_a || q.conv_b)) {
+                    uint8_t* sa = tile_base + s * stage_bytes;
+                    if (q.conv_a) convert(sa, kABytes, kABytes);
+                    if (q.conv_b) convert(sa + 2 * kABytes, kBBytes, kBBytes);
+                    fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's reads
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CTAS == 1) mbar_arrive(&ready_bar[s]);
+                    else mbar_arrive_cluster(ready_addr + s * (uint32_t)sizeof(uint64_t));
+                }
             }
         }
     } else {
@@ -728,9 +768,11 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     { const int r = tc_sm_reserve(); if (r > 0 && sm_count - r >= 8) sm_count -= r; }
     CLICA_REQUIRE(g.Mo >= 1 && g.No >= 1 && g.Kr >= 1, CLICA_E_BADARG, "tc_gemm: empty problem");
     CLICA_REQUIRE(g.A.hi && g.B.hi, CLICA_E_BADARG, "tc_gemm: null operand");
-    CLICA_REQUIRE((g.A.lo != nullptr) == (g.B.lo != nullptr), CLICA_E_BADARG, "tc_gemm: operands must both be split or both plain");
     CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
-    const int nterms = g.A.lo ? 3 : 1;
+    // 3xTF32 when asked for (g.nterms == 3) or when any operand comes as a (hi, lo) pair; an operand WITHOUT a lo
+    // plane is then split inside the kernel by the converter warps
+    const int nterms = (g.nterms == 3 || g.A.lo || g.B.lo) ? 3 : 1;
+    const int conv_a = (nterms == 3 && !g.A.lo) ? 1 : 0, conv_b = (nterms == 3 && !g.B.lo) ? 1 : 0;
     const int nplanes = (nterms == 3) ? 2 : 1;
     // CTA pairs (tcgen05 cta_group::2) whenever the output has more than one 128-row tile; CLICA_TC_PAIR=0 disables
     //   1: always;  2: only where the isolated per-shape timings favoured pairs (tools/gemm_bench.py): weight-gradient
@@ -752,12 +794,9 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     const int b_rows = g.b_mn_major ? g.Kr : g.No, b_cols = g.b_mn_major ? g.No : g.Kr, b_box = g.b_mn_major ? BK : bnl;
     if ((rc = get_tensor_map(g.A.hi, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAh))) return rc;
     if ((rc = get_tensor_map(g.B.hi, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBh))) return rc;
-    if (nterms == 3) {
-        if ((rc = get_tensor_map(g.A.lo, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAl))) return rc;
-        if ((rc = get_tensor_map(g.B.lo, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBl))) return rc;
-    } else {
-        tAl = tAh; tBl = tBh;
-    }
+    tAl = tAh; tBl = tBh;
+    if (g.A.lo && (rc = get_tensor_map(g.A.lo, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAl))) return rc;
+    if (g.B.lo && (rc = get_tensor_map(g.B.lo, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBl))) return rc;
     // planar outputs are written by TMA stores of 32 x 32 blocks (clipped to [Mo x No] by the map)
     tOh = tAh; tOl = tAh;
     if (g.outp.hi && (rc = get_tensor_map(g.outp.hi, g.Mo, g.No, g.outp.ld, 32, false, &tOh))) return rc;
@@ -770,7 +809,7 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     }
     q.Mo = g.Mo; q.No = g.No;
     q.kb_total = ceil_div(g.Kr, BK);
-    q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms;
+    q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms; q.conv_a = conv_a; q.conv_b = conv_b;
     const size_t stage_bytes = (size_t)nplanes * (BM + bnl) * BK * 4;
     const size_t smem_cap = 227 * 1024 - 2048;                  // static shared memory (barriers, bias slice) + slack
     const size_t smem_fixed = 1024 + kEpiStageBytes;            // alignment slack + 8 x 4 KB epilogue staging

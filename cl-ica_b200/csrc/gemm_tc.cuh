@@ -3,6 +3,9 @@
 // Operands are "planar": a matrix is one fp32 plane (TF32 mode: the hardware drops the low 13 mantissa bits)
 // or a (hi, lo) pair of planes with  value = hi + lo,  hi exactly representable in tf32 (3xTF32 mode:
 // D += A_hi B_hi + A_lo B_hi + A_hi B_lo  -- three tensor-core MMAs per product, ~2^-21 relative error).
+// In 3xTF32 mode an operand may also be given as ONE fp32 plane (lo == nullptr with TcGemm::nterms == 3): the kernel's
+// converter warps then produce the (hi, lo) pair in shared memory, tile by tile, after the TMA delivered the fp32 data
+// -- activations and gradients are stored that way (half the HBM / L2 bytes), weights are pre-split once per step.
 #pragma once
 #include "common.cuh"
 
@@ -28,6 +31,7 @@ struct TcGemm {
     float* out; int ldo;          // plain fp32 output (nullable unless epi == kTcAtomic)
     PlanesOut outp;               // planar output (hi = round-to-tf32(v), lo = v - hi), nullable
     int allow_split_k;            // epi == kTcAtomic only
+    int nterms;                   // 3: 3xTF32 even when an operand has no lo plane (it is split inside the kernel); 0: infer
     float* colsum;                // optional [No]: += column sums of the stored values (caller zeroes it first)
 };
 

@@ -184,13 +184,21 @@ struct MlpPlan {
     int L; const int* w; int M; int mode;
     int nplanes;                     // planes per hidden activation (2 in 3xTF32 mode, else 1)
     bool planar;                     // hidden activations use plane_ld() pitches
+    // Hidden activations and the gradients flowing between layers are ONE fp32 plane in every mode: in 3xTF32 mode
+    // the tensor-core kernel splits them into (hi, lo) in shared memory (gemm_tc.cu, converter warps); only the
+    // weights are pre-split (nplanes planes, once per optimizer step).
     bool layer_eligible(int l) const {      // M-independent: decides the packed-weight layout
-        return tc_mode(mode) && l > 0 && l < L - 1 && tc_shape_ok(32, w[l + 1], w[l]);
+        if (!tc_mode(mode) || !tc_shape_ok(32, w[l + 1], w[l])) return false;
+        // first / last layer: the dense input / output rows must be legal TMA strides (multiples of 16 bytes)
+        if (l == 0 && (w[0] % 4) != 0) return false;
+        if (l == L - 1 && (w[L] % 4) != 0) return false;
+        return true;
     }
     bool layer_tc(int l) const { return layer_eligible(l) && tc_shape_ok(M, w[l + 1], w[l]); }
     int act_ld(int l) const { return planar ? plane_ld(w[l]) : w[l]; }
-    size_t act_floats(int l) const { return (size_t)nplanes * M * act_ld(l); }
+    size_t act_floats(int l) const { return (size_t)M * act_ld(l); }
     size_t wplane_floats(int l) const { return layer_eligible(l) ? (size_t)nplanes * w[l + 1] * plane_ld(w[l]) : 0; }
+    int nterms() const { return mode == CLICA_GEMM_3XTF32 ? 3 : 1; }
 };
 MlpPlan make_plan(int L, const int* widths, int M, int mode) {
     MlpPlan p;
@@ -201,10 +209,8 @@ MlpPlan make_plan(int L, const int* widths, int M, int mode) {
 }
 PlanesIn act_in(const MlpPlan& p, const float* const* acts, int l) {
     PlanesIn a;
-    if (l == 0 || l == p.L) { a.hi = acts[l]; a.lo = nullptr; a.ld = p.w[l]; return a; }
-    a.ld = p.act_ld(l);
-    a.hi = acts[l];
-    a.lo = (p.nplanes == 2) ? acts[l] + (size_t)p.M * a.ld : nullptr;
+    a.hi = acts[l]; a.lo = nullptr;
+    a.ld = (l == 0 || l == p.L) ? p.w[l] : p.act_ld(l);
     return a;
 }
 PlanesOut as_out(PlanesIn a) { PlanesOut o; o.hi = (float*)a.hi; o.lo = (float*)a.lo; o.ld = a.ld; return o; }
@@ -327,7 +333,7 @@ extern "C" int clica_linear_bwd_weight(const float* dy, int lddy, const float* x
 extern "C" size_t clica_mlp_act_floats(int M, int width, int mode) {
     if (M < 1 || width < 1) return 0;
     if (!tc_mode(mode)) return (size_t)M * width;
-    return (size_t)((mode == CLICA_GEMM_3XTF32) ? 2 : 1) * M * plane_ld(width);
+    return (size_t)M * plane_ld(width);        // one fp32 plane in every tensor-core mode (see MlpPlan)
 }
 
 extern "C" size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode) {
@@ -373,10 +379,11 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
         const float s = (l == L - 1) ? 1.f : slope;
         PlanesIn x = act_in(p, acts, l);
         PlanesOut y = as_out(act_in(p, acts, l + 1));
-        if (p.layer_tc(l)) {
+        if (p.layer_tc(l) && aligned16(x.hi) && aligned16(y.hi)) {
             TcGemm g = {};
-            g.A = x; g.a_mn_major = 0; g.B = weight_planes(p, w, l); g.b_mn_major = 0;
-            g.Mo = M; g.No = N; g.Kr = K; g.epi = kTcBiasAct; g.bias = b[l]; g.slope = s; g.outp = y;
+            g.A = x; g.a_mn_major = 0; g.B = weight_planes(p, w, l); g.b_mn_major = 0; g.nterms = p.nterms();
+            g.Mo = M; g.No = N; g.Kr = K; g.epi = kTcBiasAct; g.bias = b[l]; g.slope = s;
+            g.outp = y;        // one fp32 plane through the TMA (the dense [M, N] output of the last layer as well)
             rc = tc_gemm_launch(g, di.sm_count, st);
         } else {
             rc = simt_fwd(x, W[l], K, b[l], y, M, K, N, s, di.sm_count, st);
@@ -422,17 +429,18 @@ extern "C" int clica_mlp_bwd_range(int L, const int* widths, const float* const*
     if (l_first < L - 1) {                        // continue where the previous range stopped
         g.ld = p.act_ld(l_first + 1);
         g.hi = w.gbuf[(l_first + 1) & 1];
-        g.lo = (p.nplanes == 2) ? g.hi + (size_t)M * g.ld : nullptr;
+        g.lo = nullptr;
         db_done = true;
     }
     for (int l = l_first; l >= l_last; --l) {
         const int K = widths[l], N = widths[l + 1];
         PlanesIn x = act_in(p, acts, l);
         // dW[l] = g^T x ; db[l] = column sums of g
-        if (p.layer_tc(l)) {
+        const bool tc_l = p.layer_tc(l) && aligned16(g.hi) && aligned16(x.hi);
+        if (tc_l) {
             if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(dW[l], 0, (size_t)N * K * sizeof(float), st));
             TcGemm t = {};
-            t.A = g; t.a_mn_major = 1; t.B = x; t.b_mn_major = 1;
+            t.A = g; t.a_mn_major = 1; t.B = x; t.b_mn_major = 1; t.nterms = p.nterms();
             t.Mo = N; t.No = K; t.Kr = M; t.epi = kTcAtomic; t.out = dW[l]; t.ldo = K; t.allow_split_k = 1;
             if ((rc = tc_gemm_launch(t, di.sm_count, st))) return rc;
             if (!db_done && (rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st, pz))) return rc;
@@ -448,12 +456,12 @@ extern "C" int clica_mlp_bwd_range(int L, const int* widths, const float* const*
         PlanesOut gp;
         gp.ld = p.act_ld(l);
         gp.hi = w.gbuf[l & 1];
-        gp.lo = (p.nplanes == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
+        gp.lo = nullptr;
         // the epilogue that writes g_prev also accumulates its column sums = db[l-1] (no separate reduction pass)
         if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
-        if (p.layer_tc(l)) {
+        if (tc_l) {
             TcGemm t = {};
-            t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1;
+            t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1; t.nterms = p.nterms();
             t.Mo = M; t.No = K; t.Kr = N; t.epi = kTcMask; t.aux = x.hi; t.ldaux = x.ld; t.slope = slope; t.outp = gp;
             t.colsum = db[l - 1];
             rc = tc_gemm_launch(t, di.sm_count, st);
