@@ -41,6 +41,7 @@ struct TcKernelParams {
     int kb_total, kb_per_split, splits;
     int a_mn, b_mn, nterms, stages;
     int conv_a, conv_b;               // 3xTF32 with a single stored fp32 plane: the converter warps split it in shared memory
+    int conv_trunc;                   // split by truncation (hi = the landed word as the tensor core reads it); 0: by rounding
     int epi;
     const float* bias; float slope;
     const float* aux; int ldaux;
@@ -376,13 +377,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     } else if (warp >= 10) {
         // ===== operand converters: warps 10..13.  3xTF32 operands that live in HBM as ONE fp32 plane (activations and
         // their gradients: half the DRAM / L2 bytes of a stored (hi, lo) pair) are split here, in shared memory, right
-        // after the TMA delivered them: hi = tf32-round(v) overwrites the tile in place, lo = tf32-round(v - hi) goes to
-        // the stage's lo slot at the same offset -- the layout (K-major / MN-major swizzle) is irrelevant to an
-        // element-wise pass, and the values are bit-identical to planes split by split_planes_kernel.
+        // after the TMA delivered them; lo goes to the stage's lo slot at the same offset -- the layout (K-major /
+        // MN-major swizzle) is irrelevant to an element-wise pass.
         const int ctid = threadIdx.x - 320;
         uint8_t* const tile_base = smem_raw + (tiles - smem_u32(smem_raw));
+        // q.conv_trunc (default): the tensor core reads an fp32 word as tf32 by IGNORING its low 13 mantissa bits, so the
+        // landed tile already is the hi operand (hi = v with those bits cleared) and only lo = v - hi has to be produced:
+        // one AND + one subtraction per element, one store per 16 bytes; lo's own low bits are dropped by the same
+        // truncation (2^-24 relative).  conv_trunc == 0 reproduces split_planes_kernel bit for bit (hi = tf32-round(v)
+        // written back in place, lo = tf32-round(v - hi)) at four times the instruction count.
+        constexpr uint32_t kStep = (uint32_t)kConvWarps * 32u * 16u;
         auto convert = [&](uint8_t* src, uint32_t bytes, uint32_t lo_off) {
-            for (uint32_t i = (uint32_t)ctid * 16u; i < bytes; i += (uint32_t)kConvWarps * 32u * 16u) {
+            if (q.conv_trunc) {
+                for (uint32_t i = (uint32_t)ctid * 16u; i < bytes; i += 4u * kStep) {     // 4 independent chunks in flight
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i + u * kStep < bytes) v[u] = *reinterpret_cast<const float4*>(src + i + u * kStep);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (i + u * kStep >= bytes) continue;
+                        float4 l;
+                        l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u);
+                        l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u);
+                        l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u);
+                        l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4*>(src + i + u * kStep + lo_off) = l;
+                    }
+                }
+                return;
+            }
+            for (uint32_t i = (uint32_t)ctid * 16u; i < bytes; i += kStep) {
                 const float4 v = *reinterpret_cast<const float4*>(src + i);
                 float4 h, l;
                 h.x = round_to_tf32(v.x); h.y = round_to_tf32(v.y); h.z = round_to_tf32(v.z); h.w = round_to_tf32(v.w);
@@ -810,6 +835,7 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     q.Mo = g.Mo; q.No = g.No;
     q.kb_total = ceil_div(g.Kr, BK);
     q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms; q.conv_a = conv_a; q.conv_b = conv_b;
+    q.conv_trunc = env_int("CLICA_TC_CONV_TRUNC", 1);
     const size_t stage_bytes = (size_t)nplanes * (BM + bnl) * BK * 4;
     const size_t smem_cap = 227 * 1024 - 2048;                  // static shared memory (barriers, bias slice) + slack
     const size_t smem_fixed = 1024 + kEpiStageBytes;            // alignment slack + 8 x 4 KB epilogue staging

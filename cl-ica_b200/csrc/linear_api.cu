@@ -196,7 +196,9 @@ struct MlpPlan {
     }
     bool layer_tc(int l) const { return layer_eligible(l) && tc_shape_ok(M, w[l + 1], w[l]); }
     int act_ld(int l) const { return planar ? plane_ld(w[l]) : w[l]; }
-    size_t act_floats(int l) const { return (size_t)M * act_ld(l); }
+    // CLICA_TC_SINGLE_PLANE=0 restores stored (hi, lo) activation planes (round-1 layout; A/B measurements)
+    int act_planes() const { return (mode == CLICA_GEMM_3XTF32 && env_flag("CLICA_TC_SINGLE_PLANE", 1) == 0) ? 2 : 1; }
+    size_t act_floats(int l) const { return (size_t)act_planes() * M * act_ld(l); }
     size_t wplane_floats(int l) const { return layer_eligible(l) ? (size_t)nplanes * w[l + 1] * plane_ld(w[l]) : 0; }
     int nterms() const { return mode == CLICA_GEMM_3XTF32 ? 3 : 1; }
 };
@@ -211,6 +213,7 @@ PlanesIn act_in(const MlpPlan& p, const float* const* acts, int l) {
     PlanesIn a;
     a.hi = acts[l]; a.lo = nullptr;
     a.ld = (l == 0 || l == p.L) ? p.w[l] : p.act_ld(l);
+    if (l != 0 && l != p.L && p.act_planes() == 2) a.lo = acts[l] + (size_t)p.M * a.ld;
     return a;
 }
 PlanesOut as_out(PlanesIn a) { PlanesOut o; o.hi = (float*)a.hi; o.lo = (float*)a.lo; o.ld = a.ld; return o; }
@@ -333,7 +336,8 @@ extern "C" int clica_linear_bwd_weight(const float* dy, int lddy, const float* x
 extern "C" size_t clica_mlp_act_floats(int M, int width, int mode) {
     if (M < 1 || width < 1) return 0;
     if (!tc_mode(mode)) return (size_t)M * width;
-    return (size_t)M * plane_ld(width);        // one fp32 plane in every tensor-core mode (see MlpPlan)
+    const int planes = (mode == CLICA_GEMM_3XTF32 && env_flag("CLICA_TC_SINGLE_PLANE", 1) == 0) ? 2 : 1;
+    return (size_t)planes * M * plane_ld(width);        // one fp32 plane by default (see MlpPlan)
 }
 
 extern "C" size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode) {
@@ -429,7 +433,7 @@ extern "C" int clica_mlp_bwd_range(int L, const int* widths, const float* const*
     if (l_first < L - 1) {                        // continue where the previous range stopped
         g.ld = p.act_ld(l_first + 1);
         g.hi = w.gbuf[(l_first + 1) & 1];
-        g.lo = nullptr;
+        g.lo = (p.act_planes() == 2) ? g.hi + (size_t)M * g.ld : nullptr;
         db_done = true;
     }
     for (int l = l_first; l >= l_last; --l) {
@@ -456,7 +460,7 @@ extern "C" int clica_mlp_bwd_range(int L, const int* widths, const float* const*
         PlanesOut gp;
         gp.ld = p.act_ld(l);
         gp.hi = w.gbuf[l & 1];
-        gp.lo = nullptr;
+        gp.lo = (p.act_planes() == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
         // the epilogue that writes g_prev also accumulates its column sums = db[l-1] (no separate reduction pass)
         if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
         if (tc_l) {

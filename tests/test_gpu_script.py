@@ -76,3 +76,18 @@ def test_config2_script_with_device_samplers(cuda_device, tmp_path):
         json.dump({"device_samplers_ms_per_step": dt_dev * 1e3, "host_samplers_ms_per_step": dt_host * 1e3,
                    "pairs_per_s_device_samplers": 6144 / dt_dev, "pairs_per_s_host_samplers": 6144 / dt_host}, fh)
     assert dt_dev <= 1.1 * dt_host
+
+
+def test_config4_conv_encoder_step_matches_the_reference_loss(cuda_device, tmp_path):
+    """BASELINE config 4: the reference's own 64x64 ConvNet (kitti_masks/model.py:28-56, via cuDNN) feeding
+    the fused loss through strided views, as kitti_masks/solver.py:60-75 does; 5-step loss trajectory vs the reference."""
+    sys.path.insert(0, ROOT)
+    from clica_b200 import vendor
+    if vendor.vendored_dir() is None:
+        pytest.skip("baseline/_ref is absent")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config4_bench.py"), "--batch", "256", "--steps", "3",
+                          "--out", str(tmp_path / "c4.json")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    with open(tmp_path / "c4.json") as fh:
+        d = json.load(fh)
+    assert d["max_rel_loss_diff_first_5_steps"] <= 1e-4

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""BASELINE config 4: ConvNet encoder on 64x64x3 synthetic images, z-dim 10, batch 1024, 1xB200.
+
+The encoder is the reference's own 64x64 ConvNet, `kitti_masks/model.py:28-56` (BetaVAE_H, nc=3, z_dim=10), imported
+UNMODIFIED from baseline/_ref and run by torch / cuDNN (convolutions are library code, out of the hot path); the step is
+the one of `kitti_masks/solver.py:60-75`:  mu = net(x); z1 = mu[::2]; z2 = mu[1::2]; z3 = roll(z1); loss; backward; Adam.
+Two arms on the same GPU, same weights, same images:
+  reference  losses.LpSimCLRLoss of baseline/_ref (torch eager: materialises B x B x d)
+  ours       the drop-in LpSimCLRLoss (fused CUDA kernels; consumes the strided views mu[::2], mu[1::2] in place)
+Prints one JSON object: per-arm ms/step, pairs/s, images/s, loss agreement over the trajectory.
+
+    python tools/config4_bench.py [--batch 1024] [--p 1] [--steps 30] [--out gpurun_out/config4.json]
+"""
+import argparse
+import copy
+import importlib.util
+import json
+import os
+import sys
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def load_ref(ref, rel, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ref, rel))
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1024, help="images per step (pairs = batch / 2, solver.py:64-65)")
+    ap.add_argument("--p", type=int, default=1, help="main_kitti.py's default exponent")
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    import torch
+    import clica_b200
+    from clica_b200 import vendor
+    ref = vendor.vendored_dir()
+    if ref is None:
+        raise SystemExit("baseline/_ref is absent (run __graft_entry__.build() where /root/reference exists)")
+    dev = torch.device("cuda:0")
+    sys.path.insert(0, ref)                      # kitti_masks/model.py does `import layers`
+    model = load_ref(ref, "kitti_masks/model.py", "_c4_model")
+    ref_losses = load_ref(ref, "losses.py", "_c4_ref_losses")
+    sys.path.insert(0, clica_b200.DROPIN_DIR)
+    import losses as our_losses
+    assert our_losses.LpSimCLRLoss is not ref_losses.LpSimCLRLoss
+
+    torch.manual_seed(0)
+    net0 = model.BetaVAE_H(z_dim=10, nc=3).to(dev)
+    B = args.batch
+    base = torch.rand(B // 2, 3, 64, 64, device=dev)
+    x = torch.empty(B, 3, 64, 64, device=dev)
+    x[::2] = base
+    x[1::2] = (base + 0.05 * torch.randn_like(base)).clamp(0, 1)          # a positive = a perturbed copy
+    res = {}
+    traj = {}
+    for arm, mod in (("reference", ref_losses), ("ours", our_losses)):
+        net = copy.deepcopy(net0)
+        crit = mod.LpSimCLRLoss(p=args.p, tau=1.0, simclr_compatibility_mode=True)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+
+        def step():
+            mu = net(x)
+            z1, z2 = mu[::2], mu[1::2]
+            loss, _, _ = crit(None, None, None, z1, z2, torch.roll(z1, 1, 0))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        vals = [step().item() for _ in range(5)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            last = step()
+        last.item()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        res[arm] = {"ms_per_step": dt * 1e3, "pairs_per_s": (B // 2) / dt, "images_per_s": B / dt}
+        traj[arm] = vals
+    rel = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(traj["ours"], traj["reference"]))
+    out = {"config": f"BetaVAE_H(nc=3, z_dim=10) 64x64x3 synthetic, batch {B} images ({B // 2} pairs), p={args.p}",
+           "arms": res, "first_losses": traj, "max_rel_loss_diff_first_5_steps": rel,
+           "speedup_ours_over_reference": res["reference"]["ms_per_step"] / res["ours"]["ms_per_step"]}
+    print(json.dumps(out))
+    if args.out:
+        with open(args.out, "w") as fh:
+            json.dump(out, fh, indent=1)
+    assert rel <= 1e-4, rel
+
+
+if __name__ == "__main__":
+    main()
