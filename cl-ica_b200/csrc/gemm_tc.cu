@@ -167,6 +167,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar_cluster_addr), "r"(x), "r"(y) : "memory");
+}
 // tcgen05.commit that arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -228,13 +234,19 @@ __device__ __forceinline__ int tile_width(int rem) {
     return w < BN ? w : BN;
 }
 
-template <int ROWS>
-__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar) {
+// REMOTE: pair mode without converters -- the completion is signalled on the LEADER's barrier (cluster address)
+template <int ROWS, bool REMOTE>
+__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar,
+                                             uint32_t bar_cluster) {
     if (!mn_major) {
-        tma_load_2d(dst, tm, k0, mn0, bar);
+        if constexpr (!REMOTE) tma_load_2d(dst, tm, k0, mn0, bar);
+        else tma_load_2d_pair(dst, tm, k0, mn0, bar_cluster);
     } else {
 #pragma unroll
-        for (int j = 0; j < ROWS / 32; ++j) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
+        for (int j = 0; j < ROWS / 32; ++j) {
+            if constexpr (!REMOTE) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
+            else tma_load_2d_pair(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar_cluster);
+        }
     }
 }
 
@@ -249,8 +261,14 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst
 // tensor pipe.  Only the leader CTA (cluster rank 0) issues MMAs; its "stage full" barrier collects the TMA bytes of
 // both CTAs, tcgen05.commit multicasts "stage free" / "accumulator ready" to both, and the epilogue warps of both
 // CTAs (each drains its own 128 TMEM lanes) report to the leader's "accumulator free" barrier.
-template <int BN, int CTAS>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// CONV: four extra converter warps split single-plane 3xTF32 operands in shared memory (see the converter role below);
+// the stage hand-over then is  TMA -> full barrier (per CTA) -> converters -> ready barrier (leader) -> MMA.  Measured on
+// B200 (profiles/r2_gemm_ab.md) that extra hop costs ~25 % of the main loop's throughput at 3 stages in flight, more
+// than the halved activation traffic returns, so CONV kernels are only used where an operand exists as a plain fp32
+// matrix anyway (the dense input / output side of the first and last encoder layer); hidden activations keep stored
+// (hi, lo) planes and the CONV == false kernel:  TMA -> full barrier (leader, both CTAs' bytes) -> MMA.
+template <int BN, int CTAS, bool CONV>
+__global__ void __launch_bounds__(CONV ? kTcThreads : kTcThreads - 32 * kConvWarps, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
@@ -281,6 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // every CTA's loads complete on its OWN full barrier; its converter warps wait there, split the fp32 planes
         // that were stored un-split, and arrive (remotely, for the peer) on the LEADER's ready barrier, which the MMA
         // warp waits on; the leader's accumulator-free barrier takes the 8 epilogue warps of each CTA
+        // (CONV == false, pair mode: the leader's full barrier expects the TMA bytes of BOTH CTAs -- one arrive.expect_tx
+        // by the leader's producer; the peer's loads complete_tx on it)
         for (int s = 0; s < q.stages; ++s) {
             mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps * CTAS); mbar_init(&empty_bar[s], 1);
         }
@@ -311,15 +331,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     const uint32_t s = it % (uint32_t)q.stages;
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    const uint32_t a_planes = (nplanes == 2 && !q.conv_a) ? 2u : 1u, b_planes = (nplanes == 2 && !q.conv_b) ? 2u : 1u;
-                    mbar_arrive_expect_tx(&full_bar[s], a_planes * kABytes + b_planes * kBBytes);
                     const uint32_t sa = tiles + s * stage_bytes;
                     const uint32_t sb = sa + nplanes * kABytes;
                     const int k0 = kb * BK;
-                    load_operand<BM>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s]);
-                    if (a_planes == 2) load_operand<BM>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s]);
-                    load_operand<BNL>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s]);
-                    if (b_planes == 2) load_operand<BNL>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s]);
+                    if constexpr (CONV) {
+                        const uint32_t a_planes = (nplanes == 2 && !q.conv_a) ? 2u : 1u, b_planes = (nplanes == 2 && !q.conv_b) ? 2u : 1u;
+                        mbar_arrive_expect_tx(&full_bar[s], a_planes * kABytes + b_planes * kBBytes);
+                        load_operand<BM, false>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s], 0u);
+                        if (a_planes == 2) load_operand<BM, false>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s], 0u);
+                        load_operand<BNL, false>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s], 0u);
+                        if (b_planes == 2) load_operand<BNL, false>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s], 0u);
+                    } else {
+                        constexpr bool REMOTE = (CTAS == 2);
+                        uint32_t fb = 0;                                 // pair mode: the LEADER's full barrier
+                        if constexpr (CTAS == 1) {
+                            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                        } else {
+                            // the peer's loads for this phase cannot start before its own empty barrier flipped, i.e. before
+                            // the leader's full barrier finished the previous phase: a complete_tx that overtakes this
+                            // expect_tx only drives the (signed) tx-count negative for a moment
+                            fb = mapa_u32(smem_u32(&full_bar[s]), 0u);
+                            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes * CTAS);
+                        }
+                        load_operand<BM, REMOTE>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s], fb);
+                        if (nplanes == 2) load_operand<BM, REMOTE>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s], fb);
+                        load_operand<BNL, REMOTE>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s], fb);
+                        if (nplanes == 2) load_operand<BNL, REMOTE>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s], fb);
+                    }
                     if (tm && it == 0) tm[2] = clock64();
                 }
             }
@@ -345,7 +383,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)q.stages;
                     const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
-                    if constexpr (CTAS == 1) mbar_wait(&ready_bar[s], ph); else mbar_wait_cluster(&ready_bar[s], ph);
+                    if constexpr (!CONV) mbar_wait(&full_bar[s], ph);
+                    else if constexpr (CTAS == 1) mbar_wait(&ready_bar[s], ph);
+                    else mbar_wait_cluster(&ready_bar[s], ph);
                     tcgen05_fence_after();
                     if (tm && it == 0) tm[3] = clock64();
                     const uint32_t sa = tiles + s * stage_bytes;
@@ -374,8 +414,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 if (tm) tm[4] = clock64();
             }
         }
-    } else if (warp >= 10) {
-        // ===== operand converters: warps 10..13.  3xTF32 operands that live in HBM as ONE fp32 plane (activations and
+    } else if (CONV && warp >= 10) {
+        // ===== operand converters: warps 10..13 (CONV kernels only).  3xTF32 operands that live in HBM as ONE fp32 plane (activations and
         // their gradients: half the DRAM / L2 bytes of a stored (hi, lo) pair) are split here, in shared memory, right
         // after the TMA delivered them; lo goes to the stage's lo slot at the same offset -- the layout (K-major /
         // MN-major swizzle) is irrelevant to an element-wise pass.
@@ -862,36 +902,35 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
         static PerDeviceOnce attr;
         if (first_on_this_device(attr)) {
             const int max_dyn = (int)smem_cap;
-            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-            CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+#define CLICA_TC_ATTR(BN_, C_, V_) CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN_, C_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn))
+            CLICA_TC_ATTR(128, 1, false); CLICA_TC_ATTR(192, 1, false); CLICA_TC_ATTR(256, 1, false);
+            CLICA_TC_ATTR(128, 2, false); CLICA_TC_ATTR(192, 2, false); CLICA_TC_ATTR(256, 2, false);
+            CLICA_TC_ATTR(128, 1, true); CLICA_TC_ATTR(192, 1, true); CLICA_TC_ATTR(256, 1, true);
+            CLICA_TC_ATTR(128, 2, true); CLICA_TC_ATTR(192, 2, true); CLICA_TC_ATTR(256, 2, true);
+#undef CLICA_TC_ATTR
         }
     }
     const int total = tiles * splits;
     const int units = sm_count / ctas;
     const int grid = (total < units ? total : units) * ctas;
+    const bool conv = (conv_a || conv_b);
+    const int threads = conv ? kTcThreads : kTcThreads - 32 * kConvWarps;
     {
         LaunchScope ls(st, kFamGemmTc);
-        if (ctas == 1) {
-            if (bn == 256) gemm_tc_kernel<256, 1><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
-            else if (bn == 192) gemm_tc_kernel<192, 1><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
-            else gemm_tc_kernel<128, 1><<<grid, kTcThreads, smem, st>>>(tAh, tAl, tBh, tBl, tOh, tOl, q);
-        } else {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            cudaError_t e;
-            if (bn == 256) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, 2>, tAh, tAl, tBh, tBl, tOh, tOl, q);
-            else if (bn == 192) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<192, 2>, tAh, tAl, tBh, tBl, tOh, tOl, q);
-            else e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, 2>, tAh, tAl, tBh, tBl, tOh, tOl, q);
-            CLICA_CUDA_OK(e);
-        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e;
+#define CLICA_TC_LAUNCH(BN_, C_, V_) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN_, C_, V_>, tAh, tAl, tBh, tBl, tOh, tOl, q)
+        if (ctas == 1 && !conv) { if (bn == 256) CLICA_TC_LAUNCH(256, 1, false); else if (bn == 192) CLICA_TC_LAUNCH(192, 1, false); else CLICA_TC_LAUNCH(128, 1, false); }
+        else if (ctas == 1) { if (bn == 256) CLICA_TC_LAUNCH(256, 1, true); else if (bn == 192) CLICA_TC_LAUNCH(192, 1, true); else CLICA_TC_LAUNCH(128, 1, true); }
+        else if (!conv) { if (bn == 256) CLICA_TC_LAUNCH(256, 2, false); else if (bn == 192) CLICA_TC_LAUNCH(192, 2, false); else CLICA_TC_LAUNCH(128, 2, false); }
+        else { if (bn == 256) CLICA_TC_LAUNCH(256, 2, true); else if (bn == 192) CLICA_TC_LAUNCH(192, 2, true); else CLICA_TC_LAUNCH(128, 2, true); }
+#undef CLICA_TC_LAUNCH
+        CLICA_CUDA_OK(e);
     }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;

@@ -184,9 +184,11 @@ struct MlpPlan {
     int L; const int* w; int M; int mode;
     int nplanes;                     // planes per hidden activation (2 in 3xTF32 mode, else 1)
     bool planar;                     // hidden activations use plane_ld() pitches
-    // Hidden activations and the gradients flowing between layers are ONE fp32 plane in every mode: in 3xTF32 mode
-    // the tensor-core kernel splits them into (hi, lo) in shared memory (gemm_tc.cu, converter warps); only the
-    // weights are pre-split (nplanes planes, once per optimizer step).
+    // Hidden activations and the gradients flowing between layers: stored (hi, lo) planes in 3xTF32 mode (default), or
+    // ONE fp32 plane that the tensor-core kernel splits in shared memory (CLICA_TC_SINGLE_PLANE=1; gemm_tc.cu, converter
+    // warps) -- half the HBM bytes but measured slower on B200 (profiles/r2_gemm_ab.md).  The dense input of the first
+    // layer and the dense output gradient of the last one always go through the converter kernels when those layers
+    // run on the tensor cores.  Weights are pre-split once per optimizer step.
     bool layer_eligible(int l) const {      // M-independent: decides the packed-weight layout
         if (!tc_mode(mode) || !tc_shape_ok(32, w[l + 1], w[l])) return false;
         // first / last layer: the dense input / output rows must be legal TMA strides (multiples of 16 bytes)
@@ -196,8 +198,7 @@ struct MlpPlan {
     }
     bool layer_tc(int l) const { return layer_eligible(l) && tc_shape_ok(M, w[l + 1], w[l]); }
     int act_ld(int l) const { return planar ? plane_ld(w[l]) : w[l]; }
-    // CLICA_TC_SINGLE_PLANE=0 restores stored (hi, lo) activation planes (round-1 layout; A/B measurements)
-    int act_planes() const { return (mode == CLICA_GEMM_3XTF32 && env_flag("CLICA_TC_SINGLE_PLANE", 1) == 0) ? 2 : 1; }
+    int act_planes() const { return (mode == CLICA_GEMM_3XTF32 && env_flag("CLICA_TC_SINGLE_PLANE", 0) == 0) ? 2 : 1; }
     size_t act_floats(int l) const { return (size_t)act_planes() * M * act_ld(l); }
     size_t wplane_floats(int l) const { return layer_eligible(l) ? (size_t)nplanes * w[l + 1] * plane_ld(w[l]) : 0; }
     int nterms() const { return mode == CLICA_GEMM_3XTF32 ? 3 : 1; }
@@ -336,8 +337,8 @@ extern "C" int clica_linear_bwd_weight(const float* dy, int lddy, const float* x
 extern "C" size_t clica_mlp_act_floats(int M, int width, int mode) {
     if (M < 1 || width < 1) return 0;
     if (!tc_mode(mode)) return (size_t)M * width;
-    const int planes = (mode == CLICA_GEMM_3XTF32 && env_flag("CLICA_TC_SINGLE_PLANE", 1) == 0) ? 2 : 1;
-    return (size_t)planes * M * plane_ld(width);        // one fp32 plane by default (see MlpPlan)
+    const int planes = (mode == CLICA_GEMM_3XTF32 && env_flag("CLICA_TC_SINGLE_PLANE", 0) == 0) ? 2 : 1;
+    return (size_t)planes * M * plane_ld(width);        // (hi, lo) planes by default (see MlpPlan)
 }
 
 extern "C" size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int mode) {

@@ -2,7 +2,7 @@
 # A/B of the activation layout / converter variants of the tcgen05 GEMM: parity tests + C2 / C3 step time per variant
 TAG=${1:-ab}
 O=gpurun_out; mkdir -p $O
-for V in "1 1" "1 0" "0 1"; do
+for V in "0 1" "1 1"; do
   set -- $V
   export CLICA_TC_SINGLE_PLANE=$1 CLICA_TC_CONV_TRUNC=$2
   timeout -k 10 300 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_step.py -q -m gpu -p no:cacheprovider > $O/pytest_mlp_sp$1_tr$2_${TAG}.log 2>&1
