@@ -522,7 +522,11 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
 #pragma unroll
             for (int u = 0; u < 8; ++u) ps += (P == kSim) ? -av[u] * bv[u] : abs_pow(av[u] - bv[u], q.pg);   // 0 for the padding
         }
-        const float xp = -ps * q.coef;
+        // the positive's logit: its rounded value only competes for the row maximum; its soft-max term is evaluated with
+        // the SAME fused expression the backward uses for w+ (fma(pos, -coef, -m2)), so that term / sum is reproduced
+        // exactly there even when the positive IS the maximum and |logit| ~ 1e3 (a product rounded on one side and fused
+        // on the other differs by half an ulp of the logit: 1e-4 on w+ ~ 1)
+        const float xp = __fmul_rn(-ps, q.coef);
         float M = q.include_pos ? xp : -INFINITY;
         // pass 1: row maximum over the split partials; pass 2 (partials now in L2): rescaled sum, fixed order.
         // __ldcg: the partials were written by other CTAs -- never through this SM's L1
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
 #pragma unroll
             for (int u = 0; u < 8; ++u) M = fmaxf(M, pm[u]);
         }
-        float S = q.include_pos ? exp2f(xp - M) : 0.f;
+        float S = q.include_pos ? exp2f(fmaf(ps, -q.coef, -M)) : 0.f;
         for (int s0 = 0; s0 < q.nsplit; s0 += 8) {
             float pm[8], psum[8];
 #pragma unroll
