@@ -525,9 +525,29 @@ def measure_workload(cx, wl_name, scaling, steps, warmup, full):
     # e.g. when the whole process runs under ncu): the library's CUDA events around its own launches in an eager pass
     # queued behind a device-side spin (kernel time without host launch gaps; ~3 us of event overhead per launch).
     fam_ms, fam_n, fam_src = None, None, None
+    # With programmatic dependent launch (CLICA_PDL, default on) a kernel's CTAs are resident -- and its CUPTI record
+    # runs -- while the tail of its predecessor drains, so per-kernel durations of the timed graph overlap.  The
+    # breakdown therefore comes from the SAME step recorded once more with plain stream order (identical kernels).
+    prof_step, prof_note = step_device, ""
+    pdl_on = os.environ.get("CLICA_PDL", "1") != "0"
+    graphed_prof = None
+    if graphed is not None and pdl_on:
+        os.environ["CLICA_PDL"] = "0"
+        try:
+            torch.manual_seed(0)
+            f_p = encoders.get_mlp(n, n, [10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n]).to(dev)
+            graphed_prof = GraphedTrainStep(f_p, g, crit, B_local, n, lr=1e-4, host_io=False, group=group)
+            graphed_prof.stage(z1_d, z2_d)
+            for _ in range(3):
+                graphed_prof.replay()
+            prof_step = lambda: graphed_prof.replay()[0]
+            prof_note = ", recorded without programmatic dependent launch (per-kernel durations do not overlap)"
+        finally:
+            os.environ["CLICA_PDL"] = "1"
     try:
-        fam_ms, fam_n = profile_families(step_device, min(steps, 10))
-        fam_src = "torch.profiler (CUPTI) kernel records of the timed step flavour (" + step_mode.split(" ")[0] + ")"
+        fam_ms, fam_n = profile_families(prof_step, min(steps, 10))
+        fam_src = ("torch.profiler (CUPTI) kernel records of the timed step flavour (" + step_mode.split(" ")[0] + ")"
+                   + prof_note)
     except Exception as exc:
         sys.stderr.write(f"bench.py: torch.profiler breakdown unavailable ({exc!r}); using library events\n")
     if fam_ms is None:
@@ -612,7 +632,7 @@ def measure_workload(cx, wl_name, scaling, steps, warmup, full):
     if e2e_eager_ms is not None:
         res["e2e"]["eager_dropin_ms_per_step"] = e2e_eager_ms
         res["e2e"]["eager_dropin_value"] = B_global / (e2e_eager_ms * 1e-3)
-    del graphed, f, opt
+    del graphed, graphed_prof, f, opt
     torch.cuda.empty_cache()
     return res
 

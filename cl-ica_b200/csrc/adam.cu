@@ -31,6 +31,7 @@ struct AdamArgs {
 // One thread advances the step count and refreshes the two bias-correction scalars (same double-precision
 // formulas as the host path), so that a captured graph can be replayed without any host-side state.
 __global__ void adam_tick_kernel(long long* state, float lr, float beta1, float beta2) {
+    pdl_enter();
     const long long t = state[0] + 1;
     state[0] = t;
     float* sc = reinterpret_cast<float*>(state + 1);
@@ -41,6 +42,7 @@ __global__ void adam_tick_kernel(long long* state, float lr, float beta1, float 
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+    pdl_enter();
     int t = 0;
     while (t + 1 < a.n && a.chunk_start[t + 1] <= (int)blockIdx.x) ++t;
     const long long base = (long long)((int)blockIdx.x - a.chunk_start[t]) * kChunk;
@@ -94,7 +96,7 @@ int adam_launch(int n, float* const* params, const float* const* grads, float* c
         a.dev_scalars = dev_scalars;
         a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
         if (chunks == 0) continue;
-        { LaunchScope ls(st, kFamAdam); adam_kernel<<<chunks, 256, 0, st>>>(a); }
+        { LaunchScope ls(st, kFamAdam); launch_k(adam_kernel, chunks, 256, 0, st, a); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -122,7 +124,7 @@ extern "C" int clica_adam_step_capturable(int n, float* const* params, const flo
     CLICA_REQUIRE(step_state && (((uintptr_t)step_state) & 7u) == 0, CLICA_E_ALIGN,
                   "adam_step_capturable: step_state must be an 8-byte aligned 16-byte device buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    { LaunchScope ls(st, kFamAdam); adam_tick_kernel<<<1, 1, 0, st>>>((long long*)step_state, lr, beta1, beta2); }
+    { LaunchScope ls(st, kFamAdam); launch_k(adam_tick_kernel, 1, 1, 0, st, (long long*)step_state, lr, beta1, beta2); }
     CLICA_CUDA_OK(cudaGetLastError());
     return adam_launch(n, params, grads, exp_avg, exp_avg_sq, numel, 0.f, 0.f,
                        reinterpret_cast<const float*>((long long*)step_state + 1), beta1, beta2, eps, grad_scale, st);

@@ -79,8 +79,33 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int env_flag(const char* name, int dflt);   // defined in abi.cu
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- kernel launch with programmatic dependent launch (PDL) ------------------------------------------
+// Every kernel of this library starts with pdl_wait() (griddepcontrol.wait: all memory operations of the preceding
+// kernel in the stream are complete and visible) followed by pdl_trigger(), and is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled -- and run their prologue (barrier
+// init, TMEM allocation, tensor-map fetch) -- while the tail of the preceding kernel is still draining, instead of
+// after a full kernel boundary.  Stream capture records these as programmatic edges, so the CUDA-graph step keeps
+// them.  CLICA_PDL=0 launches with plain stream order.
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = env_flag("CLICA_PDL", 1) != 0 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// programmatic dependent launch (see launch_k): wait for the preceding kernel's memory, then let the next one be scheduled
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

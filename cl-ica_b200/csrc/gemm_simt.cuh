@@ -38,6 +38,7 @@ constexpr int kSBM = 128, kSBN = 128, kSBK = 8, kSPad = 4;
 
 template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtGemmParams q) {
+    pdl_enter();
     __shared__ __align__(16) float As[2][kSBK][kSBM + kSPad];
     __shared__ __align__(16) float Bs[2][kSBK][kSBN + kSPad];
     const int tid = threadIdx.x;
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const SimtGemmParams 
 // db[n] += sum_m (hi[m, n] + lo[m, n]) over this block's row range; db pre-zeroed
 static __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int ld,
                                                       int M, int N, int rows_per_block, float* __restrict__ db) {
+    pdl_enter();
     __shared__ float red[8][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
     const int mbeg = blockIdx.y * rows_per_block, mend = min(M, mbeg + rows_per_block);

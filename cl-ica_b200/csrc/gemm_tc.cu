@@ -314,6 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if constexpr (CTAS == 2) cluster_sync_all();        // the peer's barriers are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // programmatic dependent launch: everything above (barriers, TMEM, cluster handshake) overlapped the tail of the
+    // preceding kernel; its results are complete and visible from here on
+    pdl_enter();
     if (tm && threadIdx.x == 0) tm[1] = clock64();
 
     if (warp == 0) {
@@ -653,6 +656,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 // split a plain matrix into planes; columns [cols, ld_dst) of the planes are zero-filled
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int ld_src, int rows, int cols,
                                                             float* __restrict__ hi, float* __restrict__ lo, int ld_dst) {
+    pdl_enter();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * ld_dst) return;
     const int r = (int)(idx / ld_dst), c = (int)(idx - (long long)r * ld_dst);
@@ -673,6 +677,7 @@ struct SplitMultiArgs {
     int n;
 };
 __global__ void __launch_bounds__(256) split_planes_multi_kernel(const SplitMultiArgs a) {
+    pdl_enter();
     int t = 0;
     while (t + 1 < a.n && a.block_start[t + 1] <= (int)blockIdx.x) ++t;
     const SplitJob& j = a.job[t];
@@ -804,7 +809,7 @@ bool tc_shape_ok(int M_out, int N_out, int K_red) { return M_out >= 32 && N_out 
 
 int tc_split_planes(const float* src, int ld_src, int rows, int cols, float* hi, float* lo, int ld_dst, cudaStream_t st) {
     const long long n = (long long)rows * ld_dst;
-    { LaunchScope ls(st, kFamMisc); split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ld_src, rows, cols, hi, lo, ld_dst); }
+    { LaunchScope ls(st, kFamMisc); launch_k(split_planes_kernel, (unsigned)((n + 255) / 256), 256, 0, st, src, ld_src, rows, cols, hi, lo, ld_dst); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -821,7 +826,7 @@ int tc_split_planes_multi(const SplitJob* jobs, int n, cudaStream_t st) {
         }
         a.block_start[a.n] = blocks;
         if (blocks == 0) continue;
-        { LaunchScope ls(st, kFamMisc); split_planes_multi_kernel<<<blocks, 256, 0, st>>>(a); }
+        { LaunchScope ls(st, kFamMisc); launch_k(split_planes_multi_kernel, blocks, 256, 0, st, a); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -919,10 +924,12 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
         LaunchScope ls(st, kFamGemmTc);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see launch_k (common.cuh)
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = env_flag("CLICA_PDL", 1) != 0 ? 2 : 1;
         cudaError_t e;
 #define CLICA_TC_LAUNCH(BN_, C_, V_) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN_, C_, V_>, tAh, tAl, tBh, tBl, tOh, tOl, q)
         if (ctas == 1 && !conv) { if (bn == 256) CLICA_TC_LAUNCH(256, 1, false); else if (bn == 192) CLICA_TC_LAUNCH(192, 1, false); else CLICA_TC_LAUNCH(128, 1, false); }

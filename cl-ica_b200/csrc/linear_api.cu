@@ -18,10 +18,10 @@ namespace clica {
 int simt_gemm(const SimtGemmParams& q, bool a_kc, bool b_kc, int splits, cudaStream_t st) {
     dim3 grid(ceil_div(q.N, kSBN), ceil_div(q.M, kSBM), splits);
     LaunchScope ls(st, kFamGemmSimt);
-    if (a_kc && b_kc) gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(q);
-    else if (a_kc && !b_kc) gemm_simt_kernel<true, false><<<grid, 256, 0, st>>>(q);
-    else if (!a_kc && b_kc) gemm_simt_kernel<false, true><<<grid, 256, 0, st>>>(q);
-    else gemm_simt_kernel<false, false><<<grid, 256, 0, st>>>(q);
+    if (a_kc && b_kc) launch_k(gemm_simt_kernel<true, true>, grid, 256, 0, st, q);
+    else if (a_kc && !b_kc) launch_k(gemm_simt_kernel<true, false>, grid, 256, 0, st, q);
+    else if (!a_kc && b_kc) launch_k(gemm_simt_kernel<false, true>, grid, 256, 0, st, q);
+    else launch_k(gemm_simt_kernel<false, false>, grid, 256, 0, st, q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -32,7 +32,7 @@ int simt_colsum(const float* hi, const float* lo, int ld, int M, int N, float* d
     if (ysplit > 64) ysplit = 64;
     const int rows_per_block = ceil_div(M, ysplit);
     LaunchScope ls(st, kFamMisc);
-    colsum_kernel<<<dim3(ceil_div(N, 32), ysplit), dim3(32, 8), 0, st>>>(hi, lo, ld, M, N, rows_per_block, db);
+    launch_k(colsum_kernel, dim3(ceil_div(N, 32), ysplit), dim3(32, 8), 0, st, hi, lo, ld, M, N, rows_per_block, db);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -43,8 +43,8 @@ namespace {
 int launch_skinny_kin(const SkinnyKinParams& q, cudaStream_t st) {
     const dim3 grid(ceil_div(q.M, kKinRows), ceil_div(q.N, kKinCols));
     LaunchScope ls(st, kFamGemmSimt);
-    if (q.K <= 16) skinny_kin_kernel<16><<<grid, 256, 0, st>>>(q);
-    else skinny_kin_kernel<48><<<grid, 256, 0, st>>>(q);
+    if (q.K <= 16) launch_k(skinny_kin_kernel<16>, grid, 256, 0, st, q);
+    else launch_k(skinny_kin_kernel<48>, grid, 256, 0, st, q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -56,7 +56,7 @@ int launch_skinny_nout_small(const SkinnyNoutParams& q, cudaStream_t st) {
                                            (int)nout_small_smem_bytes(kNsMaxN)));
     }
     LaunchScope ls(st, kFamGemmSimt);
-    skinny_nout_small_kernel<<<ceil_div(q.M, kNsRows), 256, smem, st>>>(q);
+    launch_k(skinny_nout_small_kernel, ceil_div(q.M, kNsRows), 256, smem, st, q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -71,8 +71,8 @@ int launch_skinny_nout(const SkinnyNoutParams& q, int sm_count, cudaStream_t st)
         CLICA_CUDA_OK(cudaFuncSetAttribute(skinny_nout_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     }
     LaunchScope ls(st, kFamGemmSimt);
-    if (q.N <= 16) skinny_nout_kernel<16><<<grid, 256, smem, st>>>(q);
-    else skinny_nout_kernel<48><<<grid, 256, smem, st>>>(q);
+    if (q.N <= 16) launch_k(skinny_nout_kernel<16>, grid, 256, smem, st, q);
+    else launch_k(skinny_nout_kernel<48>, grid, 256, smem, st, q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -90,9 +90,9 @@ int launch_skinny_dw(const SkinnyDwParams& q, int sm_count, cudaStream_t st) {
         // two tiles per CTA (halves the atomics of the tile-at-a-time kernel) unless that leaves > 2 CTAs per SM
         int per_cta = ceil_div(tiles, 2 * sm_count);
         if (per_cta < 2) per_cta = 2;
-        skinny_dw_small_kernel<<<ceil_div(tiles, per_cta), 256, smem, st>>>(q);
+        launch_k(skinny_dw_small_kernel, ceil_div(tiles, per_cta), 256, smem, st, q);
     } else {
-        skinny_dw_kernel<<<tiles, 256, smem, st>>>(q);
+        launch_k(skinny_dw_kernel, tiles, 256, smem, st, q);
     }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;

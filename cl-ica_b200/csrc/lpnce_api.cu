@@ -18,6 +18,7 @@ struct PrepParams {
     float default_g;                  // used when g_mean == nullptr
 };
 __global__ void lpnce_prep_kernel(const PrepParams q) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n) return;
     float gl = (q.g_mean ? *q.g_mean : q.default_g) * q.inv_count;
@@ -40,6 +41,7 @@ struct ReduceParams {
     int rows; int d; int TW; float p; int sim;
 };
 __global__ void lpnce_reduce_kernel(const ReduceParams q) {
+    pdl_enter();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)q.rows * q.d) return;
     const int row = (int)(idx / q.d), c = (int)(idx - (long long)row * q.d);
@@ -313,7 +315,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         pp.inv_count = 1.f / (float)B;
         pp.tau = tau; pp.alpha = alpha; pp.include_pos = include_pos;
         pp.E = w.E; pp.CP = w.CP; pp.default_g = 0.f;
-        { LaunchScope ls(st, kFamLossAux); lpnce_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(pp); }
+        { LaunchScope ls(st, kFamLossAux); launch_k(lpnce_prep_kernel, ceil_div(B, 256), 256, 0, st, pp); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
 
@@ -357,7 +359,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         r.g_out = g_z1; r.ldg = ldg1; r.g_z2 = g_z2; r.ldg2 = ldg2;
         r.rows = B; r.d = d; r.TW = TW; r.p = p; r.sim = (pc == kSim) ? 1 : 0;
         const long long n = (long long)B * d;
-        { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
+        { LaunchScope ls(st, kFamLossAux); launch_k(lpnce_reduce_kernel, (unsigned)((n + 255) / 256), 256, 0, st, r); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     if (g_z3) {
@@ -368,7 +370,7 @@ extern "C" int clica_lpnce_bwd(const float* z1, int ld1, const float* z2, int ld
         r.g_out = g_z3; r.ldg = ldg3; r.g_z2 = nullptr; r.ldg2 = 0;
         r.rows = M; r.d = d; r.TW = TW; r.p = p; r.sim = (pc == kSim) ? 1 : 0;
         const long long n = (long long)M * d;
-        { LaunchScope ls(st, kFamLossAux); lpnce_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r); }
+        { LaunchScope ls(st, kFamLossAux); launch_k(lpnce_reduce_kernel, (unsigned)((n + 255) / 256), 256, 0, st, r); }
         CLICA_CUDA_OK(cudaGetLastError());
     }
     return 0;

@@ -323,6 +323,7 @@ __device__ __forceinline__ float half_norm_of_row(const float* tile_row, bool va
 // loss, row statistics -> (last row tile) the three means.  All merges run in a fixed order: deterministic.
 template <int P, int DP, int R, int CW, int F>
 __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) {
+    pdl_enter();
     constexpr bool DOT = dot_capable(P, F);
     constexpr int RW = kWarps / CW;
     constexpr int RPW = 32 / F;                // rows per warp per r
@@ -600,6 +601,7 @@ __global__ void __launch_bounds__(kThreads) lpnce_fwd_kernel(const FwdParams q) 
 // ================================ backward =========================================================
 template <int P, int DP, int R, int CW, int F>
 __global__ void __launch_bounds__(kThreads) lpnce_bwd_kernel(const BwdParams q) {
+    pdl_enter();
     constexpr bool DOT = dot_capable(P, F);
     constexpr int RW = kWarps / CW;
     constexpr int RPW = 32 / F;
@@ -880,7 +882,7 @@ int launch_fwd_pd(const FwdParams& q, dim3 grid, cudaStream_t st, int r4) {
             const size_t smem = fwd_smem_bytes(DP, R4, F);
             if (smem > 48 * 1024)
                 CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kThreads, smem, st>>>(q);
+            launch_k(kern, grid, kThreads, smem, st, q);
             CLICA_CUDA_OK(cudaGetLastError());
             return 0;
         }
@@ -889,7 +891,7 @@ int launch_fwd_pd(const FwdParams& q, dim3 grid, cudaStream_t st, int r4) {
     const size_t smem = fwd_smem_bytes(DP, R, F);
     if (smem > 48 * 1024)
         CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(q);
+    launch_k(kern, grid, kThreads, smem, st, q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -900,7 +902,7 @@ int launch_bwd_pd(const BwdParams& q, dim3 grid, cudaStream_t st) {
     const size_t smem = bwd_smem_bytes(DP, R, F);
     if (smem > 48 * 1024)
         CLICA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(q);
+    launch_k(kern, grid, kThreads, smem, st, q);
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -22,6 +22,7 @@ struct MixParams {
 
 template <int NMAX>
 __global__ void __launch_bounds__(128) mixing_fwd_kernel(const MixParams q) {
+    pdl_enter();
     extern __shared__ __align__(16) float Ws[];      // [L][n][n]
     const int nn = q.n * q.n;
     for (int l = 0; l < q.L; ++l)
@@ -80,8 +81,8 @@ extern "C" int clica_mixing_fwd(const float* x, int ldx, const float* const* W, 
     const int grid = ceil_div(M, 128);
     {
         LaunchScope ls(st, kFamGemmSimt);
-        if (n <= 16) mixing_fwd_kernel<16><<<grid, 128, smem, st>>>(q);
-        else mixing_fwd_kernel<48><<<grid, 128, smem, st>>>(q);
+        if (n <= 16) launch_k(mixing_fwd_kernel<16>, grid, 128, smem, st, q);
+        else launch_k(mixing_fwd_kernel<48>, grid, 128, smem, st, q);
     }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;

@@ -74,6 +74,7 @@ __device__ __forceinline__ float draw(const Philox& ph, const SampleParams& q, u
 }
 
 __global__ void __launch_bounds__(128) sampler_kernel(const SampleParams q) {
+    pdl_enter();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= q.rows) return;
     const Philox ph{q.seed_lo, q.seed_hi};
@@ -130,7 +131,7 @@ extern "C" int clica_sample_latents(float* out, int ld, int rows, int n, int spa
     q.mean = mean; q.ld_mean = ld_mean; q.mean_rows = mean_rows; q.scale = scale; q.p = p; q.lo = box_lo; q.hi = box_hi;
     q.seed_lo = (uint32_t)seed; q.seed_hi = (uint32_t)(seed >> 32); q.off_lo = (uint32_t)offset; q.off_hi = (uint32_t)(offset >> 32) * 65537u;
     cudaStream_t st = (cudaStream_t)stream;
-    { LaunchScope ls(st, kFamMisc); sampler_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(q); }
+    { LaunchScope ls(st, kFamMisc); launch_k(sampler_kernel, ceil_div(rows, 128), 128, 0, st, q); }
     CLICA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -49,6 +49,7 @@ constexpr int kKinCols = 128;
 
 template <int KMAX>
 __global__ void __launch_bounds__(256) skinny_kin_kernel(const SkinnyKinParams q) {
+    pdl_enter();
     __shared__ __align__(16) float Bs[KMAX][kKinCols];
     __shared__ __align__(16) float xs[kKinRows][KMAX];
     __shared__ float cs[kKinCols];
@@ -185,6 +186,7 @@ constexpr int kNsItems = kNsRows * kNsMaxN / 256;
 inline size_t nout_small_smem_bytes(int N) { return (size_t)(kNsRows + N) * (kNsKC + 1) * sizeof(float); }
 
 static __global__ void __launch_bounds__(256) skinny_nout_small_kernel(const SkinnyNoutParams q) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     constexpr int LD = kNsKC + 1;
     float* xs = sm;                       // [kNsRows][LD]
@@ -287,6 +289,7 @@ constexpr int kDwsMaxOut = 2048;
 constexpr int kDwsItems = kDwsMaxOut / 256;
 
 static __global__ void __launch_bounds__(256) skinny_dw_small_kernel(const SkinnyDwParams q) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* dys = sm;                                  // [kSkRows][N]
     float* xs = sm + kSkRows * q.N;                   // [kSkRows][K + 1]
@@ -361,6 +364,7 @@ static __global__ void __launch_bounds__(256) skinny_dw_small_kernel(const Skinn
 // one warp per row: lanes split K (coalesced), N accumulators per lane, butterfly reduction at the end
 template <int NMAX>
 __global__ void __launch_bounds__(256) skinny_nout_kernel(const SkinnyNoutParams q) {
+    pdl_enter();
     extern __shared__ __align__(16) float Ws[];      // [N][K]
     for (int idx = threadIdx.x; idx < q.N * q.K; idx += 256) {
         const int n = idx / q.K, k = idx - n * q.K;
@@ -415,6 +419,7 @@ __global__ void __launch_bounds__(256) skinny_nout_kernel(const SkinnyNoutParams
 
 // each CTA reduces a block of rows held in shared memory; one thread per (n, k) output (k == K is the bias gradient)
 static __global__ void __launch_bounds__(256) skinny_dw_kernel(const SkinnyDwParams q) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* dys = sm;                                  // [kSkRows][N]
     float* xs = sm + kSkRows * q.N;                   // [kSkRows][K + 1]
