@@ -22,6 +22,7 @@
 #include <cuda.h>   // CUtensorMap + enums only; the driver entry point is fetched through the runtime
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -36,10 +37,13 @@ constexpr int kMaxStages = 8;
 constexpr int kPairDefault = 1;                          // CLICA_TC_PAIR default (1: CTA pairs, tcgen05 cta_group::2)
 constexpr size_t kEpiStageBytes = 8 * 4096;                 // one 32 x 32 fp32 staging block per epilogue warp
 
+constexpr int kMaxChain = 12;                          // GEMMs one launch can chain (see ChainParams)
+constexpr int kMaxBN = 256;
+
 struct TcKernelParams {
     int Mo, No;
     int kb_total, kb_per_split, splits;
-    int a_mn, b_mn, nterms, stages;
+    int a_mn, b_mn, nterms;
     int conv_a, conv_b;               // 3xTF32 with a single stored fp32 plane: the converter warps split it in shared memory
     int conv_trunc;                   // split by truncation (hi = the landed word as the tensor core reads it); 0: by rounding
     int epi;
@@ -50,7 +54,33 @@ struct TcKernelParams {
     uint32_t mn_lbo, mn_sbo, mn_lt;   // MN-major descriptor fields (defaults: BK*128, 512, 1)
     float* colsum;                    // optional [No]: += column sums of the stored values (pre-zeroed by the caller)
     int out_tma;                      // kTcAtomic: tmOh describes `out`, partial sums leave as TMA reduce-adds
-    long long* timing;                // debug (tools/gemm_phase_probe.py): [grid][8] clock64 stamps of the CTA's phases
+};
+
+// One launch runs a CHAIN of GEMMs (the hidden layers of the encoder forward, or the dX / dW GEMMs of its backward) as
+// one persistent grid: the work items of all GEMMs form one list that every CTA pair walks with stride #pairs, so the
+// ramp (pipeline fill), the tail (last epilogue) and the partial last wave of a GEMM overlap the next GEMM's main loop
+// instead of being paid per kernel.  A GEMM whose operand rows are produced by an earlier GEMM of the chain waits -- per
+// 256-row block, in its TMA producer thread -- for that block's arrival counter (`flags`), which the epilogue warps of the
+// producing tiles bump once their TMA stores have completed.  Every CTA is resident (grid <= #SMs, one CTA per SM) and
+// items are processed in list order, so the earliest unfinished item can always proceed: no deadlock.
+struct ChainGemm {
+    CUtensorMap tmAh, tmAl, tmBh, tmBl, tmOh, tmOl;
+    TcKernelParams q;
+    int bn;                           // tile width of this GEMM (multiple of 32 * CTAS, <= kMaxBN)
+    int num_m, num_n, item_begin;     // tiles and the index of its first work item in the chain's list
+    int n_fastest;                    // item order: 1 = the n-tiles of one m-tile are consecutive (forward, dX: a block of
+                                      // output rows completes early); 0 = m fastest, k-split slowest (dW)
+    int dep;                          // >= 0: GEMM of the chain whose OUTPUT rows this GEMM reads as reduction-side input
+    int dep_rows;                     // 0: the rows of the item's own m-tile (A = that output); 1: the item's reduction rows
+    int dep_count;                    // arrivals of a 256-row block of `dep` that mean "all its tiles are stored"
+    int publish;                      // bump flags[this GEMM][m-tile] after each tile's stores completed
+};
+struct ChainParams {
+    ChainGemm g[kMaxChain];
+    int n, total_items, stages;
+    uint32_t stage_stride;            // bytes between ring stages (the widest GEMM's stage)
+    unsigned* flags; int flag_stride; // [n][flag_stride] arrival counters, zero at launch
+    unsigned* err;                    // set when a dependency wait timed out (logic error; the kernel never hangs)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -224,40 +254,73 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n, int m 
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// one operand tile of a stage: K-major = one {32 x ROWS} box; MN-major = ROWS/32 boxes of {32 x 32}
 // MMA width of the n-tile that starts `rem` columns before the edge of the output: a ragged last tile issues a
 // narrower MMA (multiples of 32 columns per CTA) instead of multiplying TMA zero-fill
-template <int BN, int CTAS>
-__device__ __forceinline__ int tile_width(int rem) {
+template <int CTAS>
+__device__ __forceinline__ int tile_width(int bn, int rem) {
     constexpr int G = 32 * CTAS;
     const int w = (rem + G - 1) / G * G;
-    return w < BN ? w : BN;
+    return w < bn ? w : bn;
 }
 
+// one operand tile of a stage: K-major = one {32 x rows} box (the box height is baked into the tensor map);
+// MN-major = rows/32 boxes of {32 x 32}
 // REMOTE: pair mode without converters -- the completion is signalled on the LEADER's barrier (cluster address)
-template <int ROWS, bool REMOTE>
-__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int mn0, int k0, uint64_t* bar,
-                                             uint32_t bar_cluster) {
+template <bool REMOTE>
+__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, int mn_major, int rows, int mn0, int k0,
+                                             uint64_t* bar, uint32_t bar_cluster) {
     if (!mn_major) {
         if constexpr (!REMOTE) tma_load_2d(dst, tm, k0, mn0, bar);
         else tma_load_2d_pair(dst, tm, k0, mn0, bar_cluster);
     } else {
-#pragma unroll
-        for (int j = 0; j < ROWS / 32; ++j) {
+        for (int j = 0; j < rows / 32; ++j) {
             if constexpr (!REMOTE) tma_load_2d(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar);
             else tma_load_2d_pair(dst + j * (BK * 128), tm, mn0 + 32 * j, k0, bar_cluster);
         }
     }
 }
 
-// Persistent kernel: grid = min(#work items, #SMs); a work item is (split, n-tile, m-tile) with m fastest so that
-// CTAs running side by side share the B tile in L2.  The accumulator is double-buffered in TMEM (2 x BN columns),
-// so the epilogue of item i overlaps the main loop of item i+1; the smem ring runs continuously across items.
+// ---- work list of a chain -----------------------------------------------------------------------------------
+struct Item { int m_idx, n_idx, kb0, kb1; };
+__device__ __forceinline__ Item decode_item(const ChainGemm& G, int lw) {
+    Item it;
+    int split;
+    if (G.n_fastest) { it.n_idx = lw % G.num_n; const int r = lw / G.num_n; it.m_idx = r % G.num_m; split = r / G.num_m; }
+    else { it.m_idx = lw % G.num_m; const int r = lw / G.num_m; it.n_idx = r % G.num_n; split = r / G.num_n; }
+    it.kb0 = split * G.q.kb_per_split;
+    it.kb1 = min(G.q.kb_total, it.kb0 + G.q.kb_per_split);
+    return it;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// TMA producer: the 256-row blocks [b0, b1] of the output of GEMM G.dep are completely stored (see ChainParams)
+__device__ __forceinline__ void wait_blocks(const ChainParams& P, const ChainGemm& G, int b0, int b1) {
+    const unsigned* f = P.flags + (size_t)G.dep * P.flag_stride;
+    const unsigned need = (unsigned)G.dep_count;
+    for (int b = b0; b <= b1; ++b) {
+        if (ld_acquire_u32(f + b) >= need) continue;
+        const long long t0 = clock64();
+        while (ld_acquire_u32(f + b) < need) {
+            __nanosleep(32);
+            if (clock64() - t0 > (1LL << 32)) { atomicExch(P.err, 1u); break; }     // ~2 s: a logic error must not hang the device
+        }
+    }
+    fence_proxy_async_all();       // the acquire above (generic proxy) orders the TMA reads (async proxy) that follow
+}
+
+// Persistent kernel: grid = min(#work items, #SMs); the chain's work items -- (GEMM, split, n-tile, m-tile) -- are
+// walked with stride #units by every unit (a CTA or a CTA pair).  The accumulator is double-buffered in TMEM (2 x 256
+// columns), so the epilogue of item i overlaps the main loop of item i+1; the smem ring runs continuously across items
+// and across the GEMMs of the chain.
 //
 // CTAS == 2 (CTA pair, cluster of two CTAs on the two SMs of a TPC, tcgen05 cta_group::2): a work item is a
-// 256 x BN tile.  Each CTA loads ITS 128 rows of A and ITS half (BN/2 rows) of B -- the pair's tensor cores read the
-// other half of B from the peer's shared memory -- so a CTA pulls (128 + BN/2) operand rows per k-block from L2
-// instead of (128 + BN): the kernel is paced by L2->SM operand delivery (two fp32 planes per operand), not by the
+// 256 x bn tile.  Each CTA loads ITS 128 rows of A and ITS half (bn/2 rows) of B -- the pair's tensor cores read the
+// other half of B from the peer's shared memory -- so a CTA pulls (128 + bn/2) operand rows per k-block from L2
+// instead of (128 + bn): the kernel is paced by L2->SM operand delivery (two fp32 planes per operand), not by the
 // tensor pipe.  Only the leader CTA (cluster rank 0) issues MMAs; its "stage full" barrier collects the TMA bytes of
 // both CTAs, tcgen05.commit multicasts "stage free" / "accumulator ready" to both, and the epilogue warps of both
 // CTAs (each drains its own 128 TMEM lanes) report to the leader's "accumulator free" barrier.
@@ -267,12 +330,9 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst
 // than the halved activation traffic returns, so CONV kernels are only used where an operand exists as a plain fp32
 // matrix anyway (the dense input / output side of the first and last encoder layer); hidden activations keep stored
 // (hi, lo) planes and the CONV == false kernel:  TMA -> full barrier (leader, both CTAs' bytes) -> MMA.
-template <int BN, int CTAS, bool CONV>
+template <int CTAS, bool CONV>
 __global__ void __launch_bounds__(CONV ? kTcThreads : kTcThreads - 32 * kConvWarps, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
-               const TcKernelParams q) {
+gemm_tc_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];     // this CTA's TMA bytes of the stage have landed
     __shared__ __align__(8) uint64_t ready_bar[kMaxStages];    // (leader CTA) the stage is converted in BOTH CTAs: MMA may read
@@ -280,20 +340,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float bias_s[BN];
+    __shared__ __align__(16) float bias_s[kMaxBN];
 
-    constexpr int BNL = BN / CTAS;                         // B rows this CTA loads per k-block
-    constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BNL * BK * 4;
+    constexpr uint32_t kABytes = BM * BK * 4;
+    constexpr uint32_t kAccCols = kMaxBN;                   // TMEM columns per accumulator buffer
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
     const int unit_id = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;     // a unit = one CTA or one CTA pair
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzled tiles need 1024-byte alignment
-    const int nplanes = (q.nterms == 3) ? 2 : 1;
-    const uint32_t stage_bytes = (uint32_t)nplanes * (kABytes + kBBytes);
-    const int num_m = (q.Mo + BM * CTAS - 1) / (BM * CTAS), num_n = (q.No + BN - 1) / BN;
-    const int total = num_m * num_n * q.splits;
-    long long* const tm = q.timing ? q.timing + (size_t)blockIdx.x * 8 : nullptr;
-    if (tm && threadIdx.x == 0) tm[0] = clock64();
+    const int stages = P.stages;
+    const int total = P.total_items;
 
     if (warp == 0 && lane == 0) {
         // every CTA's loads complete on its OWN full barrier; its converter warps wait there, split the fp32 planes
@@ -301,13 +357,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // warp waits on; the leader's accumulator-free barrier takes the 8 epilogue warps of each CTA
         // (CONV == false, pair mode: the leader's full barrier expects the TMA bytes of BOTH CTAs -- one arrive.expect_tx
         // by the leader's producer; the peer's loads complete_tx on it)
-        for (int s = 0; s < q.stages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps * CTAS); mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8 * CTAS); }
         fence_barrier_init();
     }
-    constexpr uint32_t kTmemCols = (BN <= 128) ? 256u : 512u;       // two accumulators; allocations are powers of two
+    constexpr uint32_t kTmemCols = 2 * kAccCols;            // two accumulators
     if (warp == 1) tmem_alloc<CTAS>(&tmem_slot, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
@@ -317,33 +373,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // programmatic dependent launch: everything above (barriers, TMEM, cluster handshake) overlapped the tail of the
     // preceding kernel; its results are complete and visible from here on
     pdl_enter();
-    if (tm && threadIdx.x == 0) tm[1] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
             uint32_t it = 0;
+            int gi = 0;
             for (int w = unit_id; w < total; w += num_units) {
-                const int m0 = (w % num_m) * (BM * CTAS) + (int)cta_rank * BM;       // this CTA's 128 rows of A
-                const int rest = w / num_m;
-                const int nt0 = (rest % num_n) * BN;
-                const int n0 = nt0 + (int)cta_rank * (tile_width<BN, CTAS>(q.No - nt0) / CTAS);   // this CTA's share of B
-                const int kb0 = (rest / num_n) * q.kb_per_split;
-                const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)q.stages;
-                    const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
+                while (gi + 1 < P.n && w >= P.g[gi + 1].item_begin) ++gi;
+                const ChainGemm& G = P.g[gi];
+                const TcKernelParams q = G.q;            // by value: registers, not re-read after every asm memory clobber
+                const Item im = decode_item(G, w - G.item_begin);
+                const int bnl = G.bn / CTAS;                                      // B rows this CTA loads per k-block
+                const uint32_t kBBytes = (uint32_t)bnl * BK * 4;
+                const uint32_t nplanes = (q.nterms == 3) ? 2u : 1u;
+                const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
+                const int m0 = im.m_idx * (BM * CTAS) + (int)cta_rank * BM;       // this CTA's 128 rows of A
+                const int nt0 = im.n_idx * G.bn;
+                const int n0 = nt0 + (int)cta_rank * (tile_width<CTAS>(G.bn, q.No - nt0) / CTAS);   // this CTA's share of B
+                if (G.dep >= 0) {
+                    if (G.dep_rows == 0) wait_blocks(P, G, im.m_idx * (BM * CTAS) / 256, (im.m_idx * (BM * CTAS) + BM * CTAS - 1) / 256);
+                    else wait_blocks(P, G, im.kb0 * BK / 256, (im.kb1 * BK - 1) / 256);
+                }
+                for (int kb = im.kb0; kb < im.kb1; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)stages;
+                    const uint32_t ph = (it / (uint32_t)stages) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    const uint32_t sa = tiles + s * stage_bytes;
+                    const uint32_t sa = tiles + s * P.stage_stride;
                     const uint32_t sb = sa + nplanes * kABytes;
                     const int k0 = kb * BK;
                     if constexpr (CONV) {
                         const uint32_t a_planes = (nplanes == 2 && !q.conv_a) ? 2u : 1u, b_planes = (nplanes == 2 && !q.conv_b) ? 2u : 1u;
                         mbar_arrive_expect_tx(&full_bar[s], a_planes * kABytes + b_planes * kBBytes);
-                        load_operand<BM, false>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s], 0u);
-                        if (a_planes == 2) load_operand<BM, false>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s], 0u);
-                        load_operand<BNL, false>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s], 0u);
-                        if (b_planes == 2) load_operand<BNL, false>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s], 0u);
+                        load_operand<false>(&G.tmAh, sa, q.a_mn, BM, m0, k0, &full_bar[s], 0u);
+                        if (a_planes == 2) load_operand<false>(&G.tmAl, sa + kABytes, q.a_mn, BM, m0, k0, &full_bar[s], 0u);
+                        load_operand<false>(&G.tmBh, sb, q.b_mn, bnl, n0, k0, &full_bar[s], 0u);
+                        if (b_planes == 2) load_operand<false>(&G.tmBl, sb + kBBytes, q.b_mn, bnl, n0, k0, &full_bar[s], 0u);
                     } else {
                         constexpr bool REMOTE = (CTAS == 2);
                         uint32_t fb = 0;                                 // pair mode: the LEADER's full barrier
@@ -356,47 +421,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             fb = mapa_u32(smem_u32(&full_bar[s]), 0u);
                             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes * CTAS);
                         }
-                        load_operand<BM, REMOTE>(&tmAh, sa, q.a_mn, m0, k0, &full_bar[s], fb);
-                        if (nplanes == 2) load_operand<BM, REMOTE>(&tmAl, sa + kABytes, q.a_mn, m0, k0, &full_bar[s], fb);
-                        load_operand<BNL, REMOTE>(&tmBh, sb, q.b_mn, n0, k0, &full_bar[s], fb);
-                        if (nplanes == 2) load_operand<BNL, REMOTE>(&tmBl, sb + kBBytes, q.b_mn, n0, k0, &full_bar[s], fb);
+                        load_operand<REMOTE>(&G.tmAh, sa, q.a_mn, BM, m0, k0, &full_bar[s], fb);
+                        if (nplanes == 2) load_operand<REMOTE>(&G.tmAl, sa + kABytes, q.a_mn, BM, m0, k0, &full_bar[s], fb);
+                        load_operand<REMOTE>(&G.tmBh, sb, q.b_mn, bnl, n0, k0, &full_bar[s], fb);
+                        if (nplanes == 2) load_operand<REMOTE>(&G.tmBl, sb + kBBytes, q.b_mn, bnl, n0, k0, &full_bar[s], fb);
                     }
-                    if (tm && it == 0) tm[2] = clock64();
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && cta_rank == 0) {
             // ===== MMA issuer (pair mode: the leader CTA drives both tensor cores) =====
-
-            const uint32_t a_step = q.a_mn ? 1024u : 32u, b_step = q.b_mn ? 1024u : 32u;   // bytes per K = 8 step
-            const uint32_t a_lbo = q.a_mn ? q.mn_lbo : 16u, b_lbo = q.b_mn ? q.mn_lbo : 16u;
-            const uint32_t a_sbo = q.a_mn ? q.mn_sbo : 1024u, b_sbo = q.b_mn ? q.mn_sbo : 1024u;
-            const uint32_t a_lt = q.a_mn ? q.mn_lt : 2u, b_lt = q.b_mn ? q.mn_lt : 2u;
             uint32_t it = 0, tile_iter = 0;
+            int gi = 0;
             for (int w = unit_id; w < total; w += num_units, ++tile_iter) {
-                const int rest = w / num_m;
-                const int kb0 = (rest / num_n) * q.kb_per_split;
-                const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
+                while (gi + 1 < P.n && w >= P.g[gi + 1].item_begin) ++gi;
+                const ChainGemm& G = P.g[gi];
+                const TcKernelParams q = G.q;            // by value: registers, not re-read after every asm memory clobber
+                const Item im = decode_item(G, w - G.item_begin);
+                const uint32_t kBBytes = (uint32_t)(G.bn / CTAS) * BK * 4;
+                const uint32_t nplanes = (q.nterms == 3) ? 2u : 1u;
+                const uint32_t a_step = q.a_mn ? 1024u : 32u, b_step = q.b_mn ? 1024u : 32u;   // bytes per K = 8 step
+                const uint32_t a_lbo = q.a_mn ? q.mn_lbo : 16u, b_lbo = q.b_mn ? q.mn_lbo : 16u;
+                const uint32_t a_sbo = q.a_mn ? q.mn_sbo : 1024u, b_sbo = q.b_mn ? q.mn_sbo : 1024u;
+                const uint32_t a_lt = q.a_mn ? q.mn_lt : 2u, b_lt = q.b_mn ? q.mn_lt : 2u;
                 const uint32_t as = tile_iter & 1u;
                 mbar_wait(&tmem_empty_bar[as], ((tile_iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + as * (uint32_t)BN;
-                const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, tile_width<BN, CTAS>(q.No - (rest % num_n) * BN), BM * CTAS);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)q.stages;
-                    const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
+                const uint32_t tmem_acc = tmem_base + as * kAccCols;
+                const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, tile_width<CTAS>(G.bn, q.No - im.n_idx * G.bn), BM * CTAS);
+                for (int kb = im.kb0; kb < im.kb1; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)stages;
+                    const uint32_t ph = (it / (uint32_t)stages) & 1u;
                     if constexpr (!CONV) mbar_wait(&full_bar[s], ph);
                     else if constexpr (CTAS == 1) mbar_wait(&ready_bar[s], ph);
                     else mbar_wait_cluster(&ready_bar[s], ph);
                     tcgen05_fence_after();
-                    if (tm && it == 0) tm[3] = clock64();
-                    const uint32_t sa = tiles + s * stage_bytes;
+                    const uint32_t sa = tiles + s * P.stage_stride;
                     const uint32_t a_hi = sa, a_lo = sa + kABytes;
                     const uint32_t b_hi = sa + nplanes * kABytes, b_lo = b_hi + kBBytes;
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        const uint32_t first = (kb > im.kb0 || ks > 0) ? 1u : 0u;
                         const uint64_t dah = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
                         const uint64_t dbh = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
                         if (nplanes == 2) {
@@ -414,7 +480,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 }
                 // accumulator complete (pair mode: each CTA's epilogue drains its own 128 TMEM lanes)
                 if constexpr (CTAS == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_pair(&tmem_full_bar[as]);
-                if (tm) tm[4] = clock64();
             }
         }
     } else if (CONV && warp >= 10) {
@@ -430,8 +495,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // truncation (2^-24 relative).  conv_trunc == 0 reproduces split_planes_kernel bit for bit (hi = tf32-round(v)
         // written back in place, lo = tf32-round(v - hi)) at four times the instruction count.
         constexpr uint32_t kStep = (uint32_t)kConvWarps * 32u * 16u;
-        auto convert = [&](uint8_t* src, uint32_t bytes, uint32_t lo_off) {
-            if (q.conv_trunc) {
+        auto convert = [&](uint8_t* src, uint32_t bytes, uint32_t lo_off, int trunc) {
+            if (trunc) {
                 for (uint32_t i = (uint32_t)ctid * 16u; i < bytes; i += 4u * kStep) {     // 4 independent chunks in flight
                     float4 v[4];
 #pragma unroll
@@ -462,18 +527,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         };
         const uint32_t ready_addr = (CTAS == 2) ? mapa_u32(smem_u32(&ready_bar[0]), 0u) : 0u;
         uint32_t it = 0;
+        int gi = 0;
         for (int w = unit_id; w < total; w += num_units) {
-            const int rest = w / num_m;
-            const int kb0 = (rest / num_n) * q.kb_per_split;
-            const int kb1 = min(q.kb_total, kb0 + q.kb_per_split);
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                const uint32_t s = it % (uint32_t)q.stages;
-                const uint32_t ph = (it / (uint32_t)q.stages) & 1u;
+            while (gi + 1 < P.n && w >= P.g[gi + 1].item_begin) ++gi;
+            const ChainGemm& G = P.g[gi];
+            const TcKernelParams q = G.q;            // by value: registers, not re-read after every asm memory clobber
+            const Item im = decode_item(G, w - G.item_begin);
+            const uint32_t kBBytes = (uint32_t)(G.bn / CTAS) * BK * 4;
+            for (int kb = im.kb0; kb < im.kb1; ++kb, ++it) {
+                const uint32_t s = it % (uint32_t)stages;
+                const uint32_t ph = (it / (uint32_t)stages) & 1u;
                 mbar_wait(&full_bar[s], ph);
-                if (nplanes == 2 && (q.conv_a || q.conv_b)) {
-                    uint8_t* sa = tile_base + s * stage_bytes;
-                    if (q.conv_a) convert(sa, kABytes, kABytes);
-                    if (q.conv_b) convert(sa + 2 * kABytes, kBBytes, kBBytes);
+                if (q.nterms == 3 && (q.conv_a || q.conv_b)) {
+                    uint8_t* sa = tile_base + s * P.stage_stride;
+                    if (q.conv_a) convert(sa, kABytes, kABytes, q.conv_trunc);
+                    if (q.conv_b) convert(sa + 2 * kABytes, kBBytes, kBBytes, q.conv_trunc);
                     fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's reads
                 }
                 __syncwarp();
@@ -495,8 +563,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int wq = warp & 3;
         const int half = ew >> 2;
         const int etid = threadIdx.x - 64;                     // 0..255 among the epilogue threads
-        const bool aux_vec = (q.aux != nullptr) && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15u) == 0);
-        uint8_t* const sbuf = smem_raw + (tiles - smem_u32(smem_raw)) + (uint32_t)q.stages * stage_bytes + (uint32_t)ew * 4096u;
+        uint8_t* const sbuf = smem_raw + (tiles - smem_u32(smem_raw)) + (uint32_t)stages * P.stage_stride + (uint32_t)ew * 4096u;
         const uint32_t sbuf_u32 = smem_u32(sbuf);
         float4* const srow = reinterpret_cast<float4*>(sbuf + lane * 128);
         // stage the warp's 32 x 32 block (thread = row, u = its 32 columns) once the previous store has read the buffer
@@ -517,16 +584,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             return t;
         };
         uint32_t tile_iter = 0;
+        int gi = 0;
         for (int w = unit_id; w < total; w += num_units, ++tile_iter) {
-            const int m0 = (w % num_m) * (BM * CTAS) + (int)cta_rank * BM;
-            const int n0 = ((w / num_m) % num_n) * BN;
+            while (gi + 1 < P.n && w >= P.g[gi + 1].item_begin) ++gi;
+            const ChainGemm& G = P.g[gi];
+            const TcKernelParams q = G.q;            // by value: registers, not re-read after every asm memory clobber
+            const Item im = decode_item(G, w - G.item_begin);
+            const int bn = G.bn, publish = G.publish;
+            const CUtensorMap* const tmOh = &G.tmOh;
+            const CUtensorMap* const tmOl = &G.tmOl;
+            const bool aux_vec = (q.aux != nullptr) && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15u) == 0);
+            const int m0 = im.m_idx * (BM * CTAS) + (int)cta_rank * BM;
+            const int n0 = im.n_idx * bn;
             const uint32_t as = tile_iter & 1u;
             const int row = m0 + wq * 32 + lane;
             const bool row_ok = row < q.Mo;
             const int rowc = row_ok ? row : (q.Mo - 1);         // clamped: loads stay in bounds, stores are predicated
             if (q.epi == kTcBiasAct) {
                 epi_bar_sync();                                 // previous tile's readers are done with bias_s
-                if (etid < BN) bias_s[etid] = (q.bias != nullptr && n0 + etid < q.No) ? __ldg(q.bias + n0 + etid) : 0.f;
+                if (etid < bn) bias_s[etid] = (q.bias != nullptr && n0 + etid < q.No) ? __ldg(q.bias + n0 + etid) : 0.f;
                 epi_bar_sync();
             }
             const float* arow = (q.aux != nullptr) ? q.aux + (size_t)rowc * q.ldaux : nullptr;
@@ -550,12 +626,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (use_aux) load_aux(half);
             mbar_wait(&tmem_full_bar[as], (tile_iter >> 1) & 1u);
             tcgen05_fence_after();
-            if (tm && etid == 0 && tile_iter == 0) tm[5] = clock64();
 #pragma unroll 1
-            for (int chunk = half; chunk < BN / 32; chunk += 2) {
+            for (int chunk = half; chunk < bn / 32; chunk += 2) {
                 float v[32];
                 __syncwarp();   // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
-                tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + as * (uint32_t)BN + (uint32_t)(chunk * 32), v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + as * kAccCols + (uint32_t)(chunk * 32), v);
                 const int col0 = n0 + chunk * 32;
                 const int nvalid = min(32, q.No - col0);
                 if (q.epi == kTcBiasAct) {
@@ -572,12 +647,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                         v[4 * j] *= av[j].x > 0.f ? 1.f : q.slope; v[4 * j + 1] *= av[j].y > 0.f ? 1.f : q.slope;
                         v[4 * j + 2] *= av[j].z > 0.f ? 1.f : q.slope; v[4 * j + 3] *= av[j].w > 0.f ? 1.f : q.slope;
                     }
-                    if (chunk + 2 < BN / 32) load_aux(chunk + 2);       // prefetch for the next iteration
+                    if (chunk + 2 < bn / 32) load_aux(chunk + 2);       // prefetch for the next iteration
                 }
                 if (nvalid <= 0) continue;                              // warp-uniform
                 if (q.epi == kTcAtomic && q.out_tma) {
                     stage(v);
-                    if (lane == 0) { tma_reduce_add_2d(&tmOh, sbuf_u32, col0, m0 + wq * 32); bulk_commit(); }
+                    if (lane == 0) { tma_reduce_add_2d(tmOh, sbuf_u32, col0, m0 + wq * 32); bulk_commit(); }
                     continue;
                 }
                 if (q.epi == kTcAtomic) {
@@ -619,14 +694,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { h[j] = round_to_tf32(v[j]); v[j] = round_to_tf32(v[j] - h[j]); }
                     stage(h);
-                    if (lane == 0) { tma_store_2d(&tmOh, sbuf_u32, col0, wrow0); bulk_commit(); }
+                    if (lane == 0) { tma_store_2d(tmOh, sbuf_u32, col0, wrow0); bulk_commit(); }
                     if (want_sum) csum = staged_colsum();
                     stage(v);
-                    if (lane == 0) { tma_store_2d(&tmOl, sbuf_u32, col0, wrow0); bulk_commit(); }
+                    if (lane == 0) { tma_store_2d(tmOl, sbuf_u32, col0, wrow0); bulk_commit(); }
                     if (want_sum) csum += staged_colsum();
                 } else {
                     stage(v);
-                    if (q.out_hi != nullptr && lane == 0) { tma_store_2d(&tmOh, sbuf_u32, col0, wrow0); bulk_commit(); }
+                    if (q.out_hi != nullptr && lane == 0) { tma_store_2d(tmOh, sbuf_u32, col0, wrow0); bulk_commit(); }
                     if (want_sum) csum = staged_colsum();
                 }
                 if (want_sum && lane < nvalid) atomicAdd(q.colsum + col0 + lane, csum);
@@ -638,7 +713,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 if constexpr (CTAS == 1) mbar_arrive(&tmem_empty_bar[as]);
                 else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0u));
             }
-            if (tm && etid == 0) tm[6] = clock64();
+            if (publish) {
+                // a later GEMM of the chain reads these rows: once every epilogue warp's stores are complete (not merely
+                // read out of shared memory), count this CTA's tile in the arrival counter of its 256-row block
+                if (lane == 0) bulk_wait_all0();
+                __syncwarp();
+                epi_bar_sync();
+                if (etid == 0) {
+                    fence_proxy_async_all();       // async-proxy (TMA) writes before the generic-proxy release below
+                    __threadfence();
+                    atomicAdd(P.flags + (size_t)gi * P.flag_stride + (m0 / 256), 1u);
+                }
+            }
         }
         if (lane == 0) bulk_wait_all0();      // the staging buffer must outlive the last bulk store
         __syncwarp();
@@ -646,7 +732,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     tcgen05_fence_before();
     __syncthreads();
     if constexpr (CTAS == 2) cluster_sync_all();    // the peer's shared memory / TMEM stay alive until both are done
-    if (tm && threadIdx.x == 0) tm[7] = clock64();
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc<CTAS>(tmem_base, kTmemCols);
@@ -832,10 +917,15 @@ int tc_split_planes_multi(const SplitJob* jobs, int n, cudaStream_t st) {
     return 0;
 }
 
-int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
-    // SMs left free for a concurrent kernel (the NCCL all-reduce of the previous gradient bucket in the multi-GPU
-    // step): a persistent grid that does not fit entirely would serialise its last CTAs behind the first ones
-    { const int r = tc_sm_reserve(); if (r > 0 && sm_count - r >= 8) sm_count -= r; }
+namespace {
+// everything tc_gemm_launch decides before the launch: tile plan, tensor maps, kernel parameters of ONE GEMM
+struct TcPrepared {
+    ChainGemm cg;
+    int ctas; bool conv;
+    size_t stage_bytes;
+    int items;
+};
+int tc_prepare(const TcGemm& g, int sm_count, TcPrepared* out) {
     CLICA_REQUIRE(g.Mo >= 1 && g.No >= 1 && g.Kr >= 1, CLICA_E_BADARG, "tc_gemm: empty problem");
     CLICA_REQUIRE(g.A.hi && g.B.hi, CLICA_E_BADARG, "tc_gemm: null operand");
     CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
@@ -857,68 +947,75 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
     const TilePlan tp = plan_tiles(g.Mo, g.No, ceil_div(g.Kr, BK), sm_count, g.epi == kTcAtomic && g.allow_split_k, ctas);
     const int bn = tp.bn;
     const int bnl = bn / ctas;                                  // B rows one CTA loads per k-block
-    CUtensorMap tAh, tAl, tBh, tBl, tOh, tOl;
+    ChainGemm& cg = out->cg;
+    memset(&cg, 0, sizeof(cg));
     int rc;
     // storage shape of each operand: K-major [MN rows][Kr cols] (box = tile rows); MN-major [Kr rows][MN cols] (box 32 rows)
     const int a_rows = g.a_mn_major ? g.Kr : g.Mo, a_cols = g.a_mn_major ? g.Mo : g.Kr, a_box = g.a_mn_major ? BK : BM;
     const int b_rows = g.b_mn_major ? g.Kr : g.No, b_cols = g.b_mn_major ? g.No : g.Kr, b_box = g.b_mn_major ? BK : bnl;
-    if ((rc = get_tensor_map(g.A.hi, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAh))) return rc;
-    if ((rc = get_tensor_map(g.B.hi, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBh))) return rc;
-    tAl = tAh; tBl = tBh;
-    if (g.A.lo && (rc = get_tensor_map(g.A.lo, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &tAl))) return rc;
-    if (g.B.lo && (rc = get_tensor_map(g.B.lo, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &tBl))) return rc;
+    if ((rc = get_tensor_map(g.A.hi, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &cg.tmAh))) return rc;
+    if ((rc = get_tensor_map(g.B.hi, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &cg.tmBh))) return rc;
+    cg.tmAl = cg.tmAh; cg.tmBl = cg.tmBh;
+    if (g.A.lo && (rc = get_tensor_map(g.A.lo, a_rows, a_cols, g.A.ld, a_box, g.a_mn_major != 0, &cg.tmAl))) return rc;
+    if (g.B.lo && (rc = get_tensor_map(g.B.lo, b_rows, b_cols, g.B.ld, b_box, g.b_mn_major != 0, &cg.tmBl))) return rc;
     // planar outputs are written by TMA stores of 32 x 32 blocks (clipped to [Mo x No] by the map)
-    tOh = tAh; tOl = tAh;
-    if (g.outp.hi && (rc = get_tensor_map(g.outp.hi, g.Mo, g.No, g.outp.ld, 32, false, &tOh))) return rc;
-    if (g.outp.lo && (rc = get_tensor_map(g.outp.lo, g.Mo, g.No, g.outp.ld, 32, false, &tOl))) return rc;
-    TcKernelParams q;
+    cg.tmOh = cg.tmAh; cg.tmOl = cg.tmAh;
+    if (g.outp.hi && (rc = get_tensor_map(g.outp.hi, g.Mo, g.No, g.outp.ld, 32, false, &cg.tmOh))) return rc;
+    if (g.outp.lo && (rc = get_tensor_map(g.outp.lo, g.Mo, g.No, g.outp.ld, 32, false, &cg.tmOl))) return rc;
+    TcKernelParams& q = cg.q;
     q.out_tma = 0;
     if (g.epi == kTcAtomic && (g.ldo % 4) == 0 && (((uintptr_t)g.out) & 15u) == 0 && env_int("CLICA_TC_RED_TMA", 1)) {
-        if ((rc = get_tensor_map(g.out, g.Mo, g.No, g.ldo, 32, false, &tOh))) return rc;
+        if ((rc = get_tensor_map(g.out, g.Mo, g.No, g.ldo, 32, false, &cg.tmOh))) return rc;
         q.out_tma = 1;
     }
     q.Mo = g.Mo; q.No = g.No;
     q.kb_total = ceil_div(g.Kr, BK);
     q.a_mn = g.a_mn_major; q.b_mn = g.b_mn_major; q.nterms = nterms; q.conv_a = conv_a; q.conv_b = conv_b;
     q.conv_trunc = env_int("CLICA_TC_CONV_TRUNC", 1);
-    const size_t stage_bytes = (size_t)nplanes * (BM + bnl) * BK * 4;
-    const size_t smem_cap = 227 * 1024 - 2048;                  // static shared memory (barriers, bias slice) + slack
-    const size_t smem_fixed = 1024 + kEpiStageBytes;            // alignment slack + 8 x 4 KB epilogue staging
-    q.stages = (int)((smem_cap - smem_fixed) / stage_bytes);
-    if (q.stages > kMaxStages) q.stages = kMaxStages;
-    { const int so = env_int("CLICA_TC_STAGES", 0); if (so >= 1 && so < q.stages) q.stages = so; }   // debug override
     q.epi = g.epi; q.bias = g.bias; q.slope = g.slope; q.aux = g.aux; q.ldaux = g.ldaux;
     q.out = g.out; q.ldo = g.ldo; q.out_hi = g.outp.hi; q.out_lo = g.outp.lo; q.ldp = g.outp.ld;
     q.mn_lbo = (uint32_t)env_int("CLICA_TC_MN_LBO", BK * 128);   // debug overrides of the MN-major descriptor
     q.mn_sbo = (uint32_t)env_int("CLICA_TC_MN_SBO", 512);
     q.mn_lt = (uint32_t)env_int("CLICA_TC_MN_LT", 1);
     q.colsum = g.colsum;
-    {   // debug: CLICA_TC_TIMING_PTR = device address (decimal) of a [grid][8] int64 buffer
-        const char* tp = getenv("CLICA_TC_TIMING_PTR");
-        q.timing = tp ? (long long*)(uintptr_t)strtoull(tp, nullptr, 0) : nullptr;
-    }
-    const int tiles = ceil_div(g.Mo, BM * ctas) * ceil_div(g.No, bn);
     int splits = tp.splits;
     q.kb_per_split = ceil_div(q.kb_total, splits);
     splits = ceil_div(q.kb_total, q.kb_per_split);
     q.splits = splits;
-    const size_t smem = (size_t)q.stages * stage_bytes + smem_fixed;
+    cg.bn = bn;
+    cg.num_m = ceil_div(g.Mo, BM * ctas);
+    cg.num_n = ceil_div(g.No, bn);
+    cg.dep = -1;
+    out->ctas = ctas;
+    out->conv = (conv_a || conv_b);
+    out->stage_bytes = (size_t)nplanes * (BM + bnl) * BK * 4;
+    out->items = cg.num_m * cg.num_n * splits;
+    return 0;
+}
+
+// one launch for the GEMMs in P (P.g[i], item_begin / dep / publish already set); flags: [n][flag_stride], zeroed here
+int tc_launch(ChainParams& P, int ctas, bool conv, size_t max_stage_bytes, int sm_count, cudaStream_t st) {
+    // SMs left free for a concurrent kernel (the NCCL all-reduce of the previous gradient bucket in the multi-GPU
+    // step): a persistent grid that does not fit entirely would serialise its last CTAs behind the first ones
+    { const int r = tc_sm_reserve(); if (r > 0 && sm_count - r >= 8) sm_count -= r; }
+    const size_t smem_cap = 227 * 1024 - 2048;                  // static shared memory (barriers, bias slice) + slack
+    const size_t smem_fixed = 1024 + kEpiStageBytes;            // alignment slack + 8 x 4 KB epilogue staging
+    P.stages = (int)((smem_cap - smem_fixed) / max_stage_bytes);
+    if (P.stages > kMaxStages) P.stages = kMaxStages;
+    { const int so = env_int("CLICA_TC_STAGES", 0); if (so >= 1 && so < P.stages) P.stages = so; }   // debug override
+    P.stage_stride = (uint32_t)max_stage_bytes;
+    const size_t smem = (size_t)P.stages * max_stage_bytes + smem_fixed;
     {   // the opt-in is per device (context)
         static PerDeviceOnce attr;
         if (first_on_this_device(attr)) {
             const int max_dyn = (int)smem_cap;
-#define CLICA_TC_ATTR(BN_, C_, V_) CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN_, C_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn))
-            CLICA_TC_ATTR(128, 1, false); CLICA_TC_ATTR(192, 1, false); CLICA_TC_ATTR(256, 1, false);
-            CLICA_TC_ATTR(128, 2, false); CLICA_TC_ATTR(192, 2, false); CLICA_TC_ATTR(256, 2, false);
-            CLICA_TC_ATTR(128, 1, true); CLICA_TC_ATTR(192, 1, true); CLICA_TC_ATTR(256, 1, true);
-            CLICA_TC_ATTR(128, 2, true); CLICA_TC_ATTR(192, 2, true); CLICA_TC_ATTR(256, 2, true);
+#define CLICA_TC_ATTR(C_, V_) CLICA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<C_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn))
+            CLICA_TC_ATTR(1, false); CLICA_TC_ATTR(2, false); CLICA_TC_ATTR(1, true); CLICA_TC_ATTR(2, true);
 #undef CLICA_TC_ATTR
         }
     }
-    const int total = tiles * splits;
     const int units = sm_count / ctas;
-    const int grid = (total < units ? total : units) * ctas;
-    const bool conv = (conv_a || conv_b);
+    const int grid = (P.total_items < units ? P.total_items : units) * ctas;
     const int threads = conv ? kTcThreads : kTcThreads - 32 * kConvWarps;
     {
         LaunchScope ls(st, kFamGemmTc);
@@ -931,15 +1028,95 @@ int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
         at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = env_flag("CLICA_PDL", 1) != 0 ? 2 : 1;
         cudaError_t e;
-#define CLICA_TC_LAUNCH(BN_, C_, V_) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN_, C_, V_>, tAh, tAl, tBh, tBl, tOh, tOl, q)
-        if (ctas == 1 && !conv) { if (bn == 256) CLICA_TC_LAUNCH(256, 1, false); else if (bn == 192) CLICA_TC_LAUNCH(192, 1, false); else CLICA_TC_LAUNCH(128, 1, false); }
-        else if (ctas == 1) { if (bn == 256) CLICA_TC_LAUNCH(256, 1, true); else if (bn == 192) CLICA_TC_LAUNCH(192, 1, true); else CLICA_TC_LAUNCH(128, 1, true); }
-        else if (!conv) { if (bn == 256) CLICA_TC_LAUNCH(256, 2, false); else if (bn == 192) CLICA_TC_LAUNCH(192, 2, false); else CLICA_TC_LAUNCH(128, 2, false); }
-        else { if (bn == 256) CLICA_TC_LAUNCH(256, 2, true); else if (bn == 192) CLICA_TC_LAUNCH(192, 2, true); else CLICA_TC_LAUNCH(128, 2, true); }
-#undef CLICA_TC_LAUNCH
+        if (ctas == 1 && !conv) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, false>, P);
+        else if (ctas == 1) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, true>, P);
+        else if (!conv) e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, false>, P);
+        else e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, true>, P);
         CLICA_CUDA_OK(e);
     }
     CLICA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st) {
+    TcPrepared pr;
+    int rc = tc_prepare(g, sm_count, &pr);
+    if (rc) return rc;
+    static thread_local ChainParams P;          // ~12 KB: kept off the stack
+    P.g[0] = pr.cg;
+    P.g[0].item_begin = 0; P.g[0].n_fastest = 0; P.g[0].dep = -1; P.g[0].publish = 0;
+    P.n = 1; P.total_items = pr.items; P.flags = nullptr; P.flag_stride = 0; P.err = nullptr;
+    return tc_launch(P, pr.ctas, pr.conv, pr.stage_bytes, sm_count, st);
+}
+
+size_t tc_chain_flag_bytes(int n_links, int max_rows) {
+    return ((size_t)n_links * (size_t)ceil_div(max_rows, 256) + 1) * sizeof(unsigned);
+}
+
+// Runs links[0..n) in order.  Maximal runs of consecutive links that all take the CTA-pair kernel without converter warps
+// are issued as ONE launch each (see ChainParams); every other link is its own launch (stream order then provides the
+// dependencies).  CLICA_TC_CHAIN=0 always launches per GEMM.
+int tc_chain_launch(const TcChainLink* links, int n, int sm_count, void* flag_ws, size_t flag_ws_bytes, cudaStream_t st) {
+    if (n <= 0) return 0;
+    CLICA_REQUIRE(n <= kTcMaxLinks, CLICA_E_BADARG, "tc_chain: %d links > %d", n, kTcMaxLinks);
+    static thread_local TcPrepared pr[kTcMaxLinks];
+    static thread_local ChainParams P;
+    const bool enabled = env_int("CLICA_TC_CHAIN", 1) != 0 && flag_ws != nullptr;
+    for (int i = 0; i < n; ++i) {
+        int rc = tc_prepare(links[i].g, sm_count, &pr[i]);
+        if (rc) return rc;
+    }
+    auto chainable = [&](int i) { return enabled && pr[i].ctas == 2 && !pr[i].conv; };
+    int i = 0;
+    while (i < n) {
+        int j = i + 1;
+        if (chainable(i)) {
+            int rows = pr[i].cg.q.Mo;
+            while (j < n && j - i < kMaxChain && chainable(j) && pr[j].cg.q.nterms == pr[i].cg.q.nterms) {
+                const int r2 = pr[j].cg.q.Mo > rows ? pr[j].cg.q.Mo : rows;
+                if (tc_chain_flag_bytes(j - i + 1, r2) > flag_ws_bytes) break;
+                rows = r2;
+                ++j;
+            }
+        }
+        const int m = j - i;
+        int max_rows = 1;
+        size_t max_stage = 0;
+        int items = 0;
+        for (int k = 0; k < m; ++k) {
+            P.g[k] = pr[i + k].cg;
+            ChainGemm& G = P.g[k];
+            G.item_begin = items;
+            items += pr[i + k].items;
+            G.n_fastest = (m > 1 && G.q.splits == 1 && G.q.epi != kTcAtomic) ? 1 : 0;
+            const int dep = links[i + k].dep;
+            CLICA_REQUIRE(dep < i + k, CLICA_E_BADARG, "tc_chain: link %d depends on a later link %d", i + k, dep);
+            G.dep = (dep >= i) ? dep - i : -1;       // a dependency outside this launch is ordered by the stream
+            G.dep_rows = links[i + k].dep_rows;
+            G.publish = 0;
+            if (G.q.Mo > max_rows) max_rows = G.q.Mo;
+            if (pr[i + k].stage_bytes > max_stage) max_stage = pr[i + k].stage_bytes;
+        }
+        bool any_dep = false;
+        for (int k = 0; k < m; ++k) {
+            ChainGemm& G = P.g[k];
+            if (G.dep < 0) continue;
+            ChainGemm& D = P.g[G.dep];
+            CLICA_REQUIRE(D.q.splits == 1 && D.q.epi != kTcAtomic, CLICA_E_BADARG, "tc_chain: a split-K GEMM cannot be a dependency");
+            D.publish = 1;
+            G.dep_count = D.num_n * 2;              // both CTAs of a pair count every tile of the 256-row block
+            any_dep = true;
+        }
+        P.n = m; P.total_items = items;
+        P.flag_stride = ceil_div(max_rows, 256);
+        P.flags = any_dep ? (unsigned*)flag_ws : nullptr;
+        P.err = any_dep ? P.flags + (size_t)m * P.flag_stride : nullptr;
+        if (any_dep) CLICA_CUDA_OK(cudaMemsetAsync(flag_ws, 0, tc_chain_flag_bytes(m, max_rows), st));
+        int rc = tc_launch(P, pr[i].ctas, pr[i].conv, max_stage, sm_count, st);
+        if (rc) return rc;
+        i = j;
+    }
     return 0;
 }
 

@@ -37,6 +37,14 @@ struct TcGemm {
 
 int tc_gemm_launch(const TcGemm& g, int sm_count, cudaStream_t st);
 
+// A chain of GEMMs issued as ONE persistent launch (gemm_tc.cu, ChainParams): link i may read -- as its A operand
+// (dep_rows = 0: the rows of each output tile) or as reduction rows (dep_rows = 1: dW = g^T x) -- the planar OUTPUT of an
+// earlier link `dep`; tiles wait per 256-row block for the producing tiles instead of for a kernel boundary.
+constexpr int kTcMaxLinks = 160;
+struct TcChainLink { TcGemm g; int dep; int dep_rows; };
+size_t tc_chain_flag_bytes(int n_links, int max_rows);      // arrival counters the chain needs (caller-provided workspace)
+int tc_chain_launch(const TcChainLink* links, int n, int sm_count, void* flag_ws, size_t flag_ws_bytes, cudaStream_t st);
+
 // ld of a plane holding `cols` columns: TMA needs 16-byte row multiples; rows padded to whole 128-byte lines make
 // every 128-byte box row exactly one L2 line (an unaligned 2000-byte pitch splits each into two requests)
 inline int plane_ld(int cols) { return (cols + 31) / 32 * 32; }

@@ -219,24 +219,29 @@ PlanesIn act_in(const MlpPlan& p, const float* const* acts, int l) {
 }
 PlanesOut as_out(PlanesIn a) { PlanesOut o; o.hi = (float*)a.hi; o.lo = (float*)a.lo; o.ld = a.ld; return o; }
 
-struct MlpWs { float* wplanes[64]; float* gbuf[2]; size_t bytes; size_t packed_bytes; };
-// `packed` (nullable): caller-provided packed weight planes (clica_mlp_pack_weights); otherwise they live in ws
+struct MlpWs { float* wplanes[64]; float* gbuf[64]; void* flags; size_t flag_bytes; size_t bytes; size_t packed_bytes; };
+// `packed` (nullable): caller-provided packed weight planes (clica_mlp_pack_weights); otherwise they live in ws.
+// gbuf[l] holds dL/d(pre-activation of layer l), l = 0 .. L-2 -- one buffer per layer, because the chained backward
+// (gemm_tc.cu, ChainParams) lets the GEMMs of neighbouring layers overlap: a ping-pong pair would be overwritten while
+// the weight-gradient GEMM of an earlier layer still reads it.
 MlpWs carve_mlp(const MlpPlan& p, void* ws, const float* packed = nullptr) {
     MlpWs w;
     char* base = (char*)ws;
     size_t off = 0, woff = 0;
-    size_t gmax = 0;
     for (int l = 0; l < p.L && l < 64; ++l) {
         w.wplanes[l] = packed ? (float*)((char*)packed + woff) : (float*)(base + woff);
         woff += align_up(p.wplane_floats(l) * sizeof(float), 1024);
-        if (l > 0 && p.act_floats(l) > gmax) gmax = p.act_floats(l);
     }
     w.packed_bytes = woff;
     off = woff;          // (the region stays reserved in ws either way: one size formula for every caller)
-    for (int k = 0; k < 2; ++k) {
-        w.gbuf[k] = (float*)(base + off);
-        off += align_up(gmax * sizeof(float), 1024);
+    for (int l = 0; l < 64; ++l) w.gbuf[l] = nullptr;
+    for (int l = 0; l + 1 < p.L && l < 64; ++l) {
+        w.gbuf[l] = (float*)(base + off);
+        off += align_up(p.act_floats(l + 1) * sizeof(float), 1024);
     }
+    w.flags = (void*)(base + off);
+    w.flag_bytes = align_up(tc_chain_flag_bytes(16, p.M), 1024);
+    off += w.flag_bytes;
     w.bytes = off;
     return w;
 }
@@ -379,6 +384,15 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
     MlpWs w = carve_mlp(p, wsa, (const float*)packed_weights);
     CLICA_REQUIRE(ws && ws_bytes >= w.bytes + 1024, CLICA_E_WORKSPACE, "mlp_fwd: workspace %zu < %zu bytes", ws_bytes, w.bytes + 1024);
     if (!packed_weights && (rc = pack_weights(p, w, W, st))) return rc;
+    // consecutive tensor-core layers are handed to tc_chain_launch together: ONE persistent launch walks their tiles, a
+    // layer's tile waiting only for the 256-row block of the previous layer's output it reads (gemm_tc.cu, ChainParams)
+    static thread_local TcChainLink links[kTcMaxLinks];
+    int nl = 0, prev_layer = -2;
+    auto flush = [&]() -> int {
+        const int r = nl ? tc_chain_launch(links, nl, di.sm_count, w.flags, w.flag_bytes, st) : 0;
+        nl = 0; prev_layer = -2;
+        return r;
+    };
     for (int l = 0; l < L; ++l) {
         const int K = widths[l], N = widths[l + 1];
         const float s = (l == L - 1) ? 1.f : slope;
@@ -389,13 +403,16 @@ extern "C" int clica_mlp_fwd(int L, const int* widths, const float* const* W, co
             g.A = x; g.a_mn_major = 0; g.B = weight_planes(p, w, l); g.b_mn_major = 0; g.nterms = p.nterms();
             g.Mo = M; g.No = N; g.Kr = K; g.epi = kTcBiasAct; g.bias = b[l]; g.slope = s;
             g.outp = y;        // one fp32 plane through the TMA (the dense [M, N] output of the last layer as well)
-            rc = tc_gemm_launch(g, di.sm_count, st);
+            if (nl == kTcMaxLinks && (rc = flush())) return rc;
+            links[nl] = TcChainLink{g, (prev_layer == l - 1) ? nl - 1 : -1, 0};
+            ++nl; prev_layer = l;
         } else {
+            if ((rc = flush())) return rc;
             rc = simt_fwd(x, W[l], K, b[l], y, M, K, N, s, di.sm_count, st);
         }
         if (rc) return rc;
     }
-    return 0;
+    return flush();
 }
 
 extern "C" int clica_mlp_bwd(int L, const int* widths, const float* const* W, const float* const* acts,
@@ -433,49 +450,72 @@ extern "C" int clica_mlp_bwd_range(int L, const int* widths, const float* const*
     bool db_done = false;                         // db[l] already accumulated by the epilogue that produced g
     if (l_first < L - 1) {                        // continue where the previous range stopped
         g.ld = p.act_ld(l_first + 1);
-        g.hi = w.gbuf[(l_first + 1) & 1];
+        g.hi = w.gbuf[l_first];
         g.lo = (p.act_planes() == 2) ? g.hi + (size_t)M * g.ld : nullptr;
         db_done = true;
     }
+    // the tensor-core GEMMs of consecutive layers -- dX_l (produces the next layer's gradient) then dW_l, l descending --
+    // are collected and issued as ONE chained launch (gemm_tc.cu, ChainParams): dX_{l-1} and dW_{l-1} wait per 256-row
+    // block for dX_l's tiles, with dW_l's tiles between them in the work list to cover that latency
+    static thread_local TcChainLink links[kTcMaxLinks];
+    int nl = 0, g_link = -1;                      // g_link: the link whose output is the current g (-1: not in the list)
+    auto flush = [&]() -> int {
+        const int r = nl ? tc_chain_launch(links, nl, di.sm_count, w.flags, w.flag_bytes, st) : 0;
+        nl = 0; g_link = -1;
+        return r;
+    };
     for (int l = l_first; l >= l_last; --l) {
         const int K = widths[l], N = widths[l + 1];
         PlanesIn x = act_in(p, acts, l);
-        // dW[l] = g^T x ; db[l] = column sums of g
         const bool tc_l = p.layer_tc(l) && aligned16(g.hi) && aligned16(x.hi);
+        if (!tc_l && (rc = flush())) return rc;
+        if (nl + 2 > kTcMaxLinks && (rc = flush())) return rc;
+        // g_prev = (g W[l]) * LeakyReLU'(pre-activation of layer l-1); acts[l] = LeakyReLU output: same sign
+        PlanesOut gp = {};
+        int dx_link = -1;
+        if (l > 0) {
+            gp.ld = p.act_ld(l);
+            gp.hi = w.gbuf[l - 1];
+            gp.lo = (p.act_planes() == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
+            // the epilogue that writes g_prev also accumulates its column sums = db[l-1] (no separate reduction pass)
+            if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
+            if (tc_l) {
+                TcGemm t = {};
+                t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1; t.nterms = p.nterms();
+                t.Mo = M; t.No = K; t.Kr = N; t.epi = kTcMask; t.aux = x.hi; t.ldaux = x.ld; t.slope = slope; t.outp = gp;
+                t.colsum = db[l - 1];
+                links[nl] = TcChainLink{t, g_link, 0};
+                dx_link = nl++;
+            }
+        }
+        // dW[l] = g^T x ; db[l] = column sums of g
         if (tc_l) {
             if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(dW[l], 0, (size_t)N * K * sizeof(float), st));
             TcGemm t = {};
             t.A = g; t.a_mn_major = 1; t.B = x; t.b_mn_major = 1; t.nterms = p.nterms();
             t.Mo = N; t.No = K; t.Kr = M; t.epi = kTcAtomic; t.out = dW[l]; t.ldo = K; t.allow_split_k = 1;
-            if ((rc = tc_gemm_launch(t, di.sm_count, st))) return rc;
-            if (!db_done && (rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st, pz))) return rc;
+            links[nl++] = TcChainLink{t, g_link, 1};
+            if (!db_done) {
+                // g is the caller's dense output gradient here (never a link's output): its column sums can run right away
+                if ((rc = simt_colsum(g.hi, g.lo, g.ld, M, N, db[l], st, pz))) return rc;
+            }
         } else {
             if ((rc = simt_bwd_weight(g, x, dW[l], K, db_done ? nullptr : db[l], M, K, N, di.sm_count, st, pz))) return rc;
         }
         if (l == 0) {
-            if (g_in) rc = simt_bwd_data(g, W[0], K, nullptr, 0, 1.f, PlanesOut{g_in, nullptr, K}, M, K, N, nullptr, st);
+            if (g_in) {
+                if ((rc = flush())) return rc;
+                rc = simt_bwd_data(g, W[0], K, nullptr, 0, 1.f, PlanesOut{g_in, nullptr, K}, M, K, N, nullptr, st);
+            }
             if (rc) return rc;
             break;
         }
-        // g_prev = (g W[l]) * LeakyReLU'(pre-activation of layer l-1); acts[l] = LeakyReLU output: same sign
-        PlanesOut gp;
-        gp.ld = p.act_ld(l);
-        gp.hi = w.gbuf[l & 1];
-        gp.lo = (p.act_planes() == 2) ? gp.hi + (size_t)M * gp.ld : nullptr;
-        // the epilogue that writes g_prev also accumulates its column sums = db[l-1] (no separate reduction pass)
-        if (!pz) CLICA_CUDA_OK(cudaMemsetAsync(db[l - 1], 0, (size_t)K * sizeof(float), st));
-        if (tc_l) {
-            TcGemm t = {};
-            t.A = g; t.a_mn_major = 0; t.B = weight_planes(p, w, l); t.b_mn_major = 1; t.nterms = p.nterms();
-            t.Mo = M; t.No = K; t.Kr = N; t.epi = kTcMask; t.aux = x.hi; t.ldaux = x.ld; t.slope = slope; t.outp = gp;
-            t.colsum = db[l - 1];
-            rc = tc_gemm_launch(t, di.sm_count, st);
-        } else {
-            rc = simt_bwd_data(g, W[l], K, x.hi, x.ld, slope, gp, M, K, N, db[l - 1], st);
+        if (!tc_l) {
+            if ((rc = simt_bwd_data(g, W[l], K, x.hi, x.ld, slope, gp, M, K, N, db[l - 1], st))) return rc;
         }
-        if (rc) return rc;
+        g_link = dx_link;
         db_done = true;
         g.hi = gp.hi; g.lo = gp.lo; g.ld = gp.ld;
     }
-    return 0;
+    return flush();
 }

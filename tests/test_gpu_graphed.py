@@ -107,7 +107,7 @@ def test_graphed_step_matches_the_eager_step(cuda_device, host_io):
     for q, q0 in zip(f_g.parameters(), init):
         assert torch.equal(q, q0)
     assert step.optimizer.device_step_count() == 0
-    assert step.launches_per_replay >= 20
+    assert step.launches_per_replay >= 12      # chained GEMM launches: 15 at these sizes (26 with CLICA_TC_CHAIN=0)
 
     opt = FusedAdam(f_e.parameters(), lr=lr)
     got, want = [], []
