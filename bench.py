@@ -538,6 +538,10 @@ def measure_workload(cx, wl_name, scaling, steps, warmup, full):
             f_p = encoders.get_mlp(n, n, [10 * n, 50 * n, 50 * n, 50 * n, 50 * n, 10 * n]).to(dev)
             graphed_prof = GraphedTrainStep(f_p, g, crit, B_local, n, lr=1e-4, host_io=False, group=group)
             graphed_prof.stage(z1_d, z2_d)
+            with torch.no_grad():              # same data regime as the timed graph: start from its current weights
+                for q_dst, q_src in zip(f_p.parameters(), f.parameters()):
+                    q_dst.copy_(q_src)
+            torch.autograd.graph.increment_version(list(f_p.parameters()))
             for _ in range(3):
                 graphed_prof.replay()
             prof_step = lambda: graphed_prof.replay()[0]

@@ -81,6 +81,8 @@ struct ChainParams {
     uint32_t stage_stride;            // bytes between ring stages (the widest GEMM's stage)
     unsigned* flags; int flag_stride; // [n][flag_stride] arrival counters, zero at launch
     unsigned* err;                    // set when a dependency wait timed out (logic error; the kernel never hangs)
+    int debug;                        // CLICA_TC_DEBUG bits (timing experiments only; results are wrong): 1 no output stores,
+                                      // 2 no column sums, 4 no mask loads
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -622,7 +624,7 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
                     }
                 }
             };
-            const bool use_aux = (q.epi == kTcMask) && (q.aux != nullptr);
+            const bool use_aux = (q.epi == kTcMask) && (q.aux != nullptr) && !(P.debug & 4);
             if (use_aux) load_aux(half);
             mbar_wait(&tmem_full_bar[as], (tile_iter >> 1) & 1u);
             tcgen05_fence_after();
@@ -650,6 +652,7 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
                     if (chunk + 2 < bn / 32) load_aux(chunk + 2);       // prefetch for the next iteration
                 }
                 if (nvalid <= 0) continue;                              // warp-uniform
+                if (P.debug & 1) continue;
                 if (q.epi == kTcAtomic && q.out_tma) {
                     stage(v);
                     if (lane == 0) { tma_reduce_add_2d(tmOh, sbuf_u32, col0, m0 + wq * 32); bulk_commit(); }
@@ -679,7 +682,7 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
                             if (j < nvalid) op[j] = v[j];
                     }
                 }
-                const bool want_sum = (q.colsum != nullptr);
+                const bool want_sum = (q.colsum != nullptr) && !(P.debug & 2);
                 if (q.out_hi == nullptr && !want_sum) continue;
                 // rows past M hold zero accumulators (TMA zero-fill) but a bias may have been added: keep them out of
                 // the column sums (the tensor map keeps them out of the stores)
@@ -1004,6 +1007,7 @@ int tc_launch(ChainParams& P, int ctas, bool conv, size_t max_stage_bytes, int s
     if (P.stages > kMaxStages) P.stages = kMaxStages;
     { const int so = env_int("CLICA_TC_STAGES", 0); if (so >= 1 && so < P.stages) P.stages = so; }   // debug override
     P.stage_stride = (uint32_t)max_stage_bytes;
+    P.debug = env_int("CLICA_TC_DEBUG", 0);
     const size_t smem = (size_t)P.stages * max_stage_bytes + smem_fixed;
     {   // the opt-in is per device (context)
         static PerDeviceOnce attr;
