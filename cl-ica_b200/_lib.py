@@ -63,6 +63,9 @@ SIGNATURES = {
                                  _i64, _c_float, _vp]),
     "clica_adam_step_capturable": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _c_float, _c_float,
                                             _c_float, _vp, _c_float, _vp]),
+    "clica_adam_step_capturable_packed": (_c_int, [_c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _c_float, _c_float,
+                                                   _c_float, _vp, _c_float, _vp, _vp, _vp, _vp, _vp]),
+    "clica_mlp_packed_weight_layout": (_c_int, [_c_int, _vp, _c_int, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -358,6 +358,26 @@ extern "C" size_t clica_mlp_packed_weight_bytes(int L, const int* widths, int mo
     return carve_mlp(p, nullptr).packed_bytes + 1024;
 }
 
+// Where clica_mlp_pack_weights puts layer l inside the packed buffer: byte offsets of its hi / lo planes (-1: the layer is
+// not packed / has no lo plane) and the planes' row pitch in floats.  Lets an optimizer keep the planes current itself
+// (clica_adam_step_capturable_packed).
+extern "C" int clica_mlp_packed_weight_layout(int L, const int* widths, int mode, long long* hi_off, long long* lo_off, int* ld) {
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    CLICA_REQUIRE(L >= 1 && L <= 64 && widths && hi_off && lo_off && ld, CLICA_E_BADARG, "mlp_packed_weight_layout: bad arguments");
+    MlpPlan p = make_plan(L, widths, 32, mode);
+    MlpWs w = carve_mlp(p, nullptr, (const float*)nullptr);
+    for (int l = 0; l < L; ++l) {
+        hi_off[l] = -1; lo_off[l] = -1; ld[l] = 0;
+        if (!p.layer_eligible(l)) continue;
+        PlanesIn wp = weight_planes(p, w, l);
+        hi_off[l] = (long long)(uintptr_t)wp.hi;
+        lo_off[l] = wp.lo ? (long long)(uintptr_t)wp.lo : -1;
+        ld[l] = wp.ld;
+    }
+    return 0;
+}
+
 extern "C" int clica_mlp_pack_weights(int L, const int* widths, const float* const* W, int mode, void* packed,
                                       size_t packed_bytes, void* stream) {
     int rc = check_mode(mode);

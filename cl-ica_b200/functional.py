@@ -22,7 +22,7 @@ _retired = []          # outgrown workspaces, kept alive (see _workspace)
 
 # ---- gradient synchronisation hook of the encoder backward (multi-GPU) ----------------------------------
 _grad_sync = None
-GRAD_BUCKET_BYTES = 2 << 20
+GRAD_BUCKET_BYTES = 2 << 20          # CLICA_GRAD_BUCKET_MB overrides (read when a backward runs)
 
 
 class grad_sync:
@@ -312,9 +312,11 @@ class _MLP(torch.autograd.Function):
                 buckets = [(L - 1, 0, 0, tot)]
             else:
                 buckets, l_first, begin = [], L - 1, 0
+                import os
+                bucket_bytes = int(float(os.environ.get("CLICA_GRAD_BUCKET_MB", GRAD_BUCKET_BYTES / 2 ** 20)) * 2 ** 20)
                 for l in range(L - 1, -1, -1):
                     end = offs_b[l] + (Ws[l].shape[0] + 3) // 4 * 4
-                    if (end - begin) * 4 >= GRAD_BUCKET_BYTES or l == 0:
+                    if (end - begin) * 4 >= bucket_bytes or l == 0:
                         buckets.append((l_first, l, begin, end))
                         l_first, begin = l - 1, end
             works = []
@@ -375,9 +377,14 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, step,
         _lib.check(rc, "clica_adam_step")
 
 
-def adam_step_capturable(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, step_state, grad_scale=1.0):
+def adam_step_capturable(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, step_state, grad_scale=1.0,
+                         pack=None):
     """Fused Adam whose step count lives on the device (``step_state``: int64[2] CUDA tensor, zero before the
-    first step).  Safe to record into a CUDA graph: every replay advances the count and applies one update."""
+    first step).  Safe to record into a CUDA graph: every replay advances the count and applies one update.
+
+    ``pack``: optional list (one entry per parameter) of ``None`` or ``(hi_ptr, lo_ptr_or_None, cols, ld)`` -- the
+    updated weight matrix is then also written in the tensor-core operand format (``packed_weight_targets``), which
+    replaces the separate re-pack pass after the step (``clica_adam_step_capturable_packed``)."""
     lib = _lib.load()
     if not params:
         return
@@ -391,10 +398,51 @@ def adam_step_capturable(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2,
     n = len(params)
     numel = (ctypes.c_int64 * n)(*[p.numel() for p in params])
     with torch.cuda.device(dev):
+        if pack is not None and any(e is not None for e in pack):
+            if len(pack) != n:
+                raise RuntimeError("adam_step_capturable: `pack` needs one entry per parameter")
+            hi, lo, cols, ld = (_vp * n)(), (_vp * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)()
+            for i, e in enumerate(pack):
+                hi[i], lo[i], cols[i], ld[i] = (None, None, 1, 1) if e is None else (e[0], e[1], int(e[2]), int(e[3]))
+            rc = lib.clica_adam_step_capturable_packed(n, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs),
+                                                       _ptr_array(exp_avg_sqs), numel, float(lr), float(beta1),
+                                                       float(beta2), float(eps), step_state.data_ptr(),
+                                                       float(grad_scale), hi, lo, cols, ld, _stream_ptr(dev))
+            _lib.check(rc, "clica_adam_step_capturable_packed")
+            return
         rc = lib.clica_adam_step_capturable(n, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs),
                                             _ptr_array(exp_avg_sqs), numel, float(lr), float(beta1), float(beta2),
                                             float(eps), step_state.data_ptr(), float(grad_scale), _stream_ptr(dev))
         _lib.check(rc, "clica_adam_step_capturable")
+
+
+def packed_weight_targets(weights, mode, packed_ptr):
+    """{weight tensor id: (hi_ptr, lo_ptr or None, cols, ld)} for the layers that live in the packed-weight buffer at
+    ``packed_ptr`` (``clica_mlp_packed_weight_layout``); layers outside it (first / last at small n) are absent."""
+    lib = _lib.load()
+    L = len(weights)
+    widths = [weights[0].shape[1]] + [W.shape[0] for W in weights]
+    cw = (ctypes.c_int * (L + 1))(*widths)
+    hi, lo, ld = (ctypes.c_longlong * L)(), (ctypes.c_longlong * L)(), (ctypes.c_int * L)()
+    _lib.check(lib.clica_mlp_packed_weight_layout(L, cw, int(mode), hi, lo, ld), "clica_mlp_packed_weight_layout")
+    out = {}
+    for l, W in enumerate(weights):
+        if hi[l] >= 0:
+            out[id(W)] = (packed_ptr + hi[l], None if lo[l] < 0 else packed_ptr + lo[l], W.shape[1], ld[l])
+    return out
+
+
+def repack_weights_into(packed_ptr, weights, mode):
+    """Re-pack ``weights`` into an existing packed buffer on the current stream (``clica_mlp_pack_weights``)."""
+    lib = _lib.load()
+    L = len(weights)
+    widths = [weights[0].shape[1]] + [W.shape[0] for W in weights]
+    cw = (ctypes.c_int * (L + 1))(*widths)
+    nbytes = lib.clica_mlp_packed_weight_bytes(L, cw, int(mode))
+    dev = weights[0].device
+    with torch.cuda.device(dev):
+        rc = lib.clica_mlp_pack_weights(L, cw, _ptr_array(list(weights)), int(mode), packed_ptr, nbytes, _stream_ptr(dev))
+        _lib.check(rc, "clica_mlp_pack_weights")
 
 
 def invalidate_packed_weights():

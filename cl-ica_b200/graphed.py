@@ -67,6 +67,13 @@ class GraphedTrainStep:
         if g is not None and os.environ.get("CLICA_FUSED_MIXING", "1") == "1":
             self._mix = F.mixing_plan(g)
         self.optimizer = FusedAdam(params, lr=lr, betas=betas, eps=eps, capturable=True)
+        # the recorded Adam step also writes the hidden layers' weights in the tensor-core operand format (no re-pack pass
+        # at the start of the next step); CLICA_ADAM_PACK=0: the graph re-packs the weights before every forward
+        self._pack_weights, self._packed_ptr, self._packed_buf, self._pack_versions = None, None, None, None
+        if os.environ.get("CLICA_ADAM_PACK", "1") == "1" and hasattr(f, "_plan"):
+            plan = f._plan()
+            if plan is not None and all(l.weight.requires_grad for l in plan[0]):
+                self._pack_weights = [l.weight for l in plan[0]]
         dev = self.device
         self.z_dev = torch.zeros((2 * self.B, self.n), dtype=torch.float32, device=dev)
         self.out_dev = torch.zeros(3, dtype=torch.float32, device=dev)
@@ -119,7 +126,16 @@ class GraphedTrainStep:
             for _ in range(warmup):          # sizes every workspace / cuBLAS handle on the capture stream
                 self._body()
             self.stream.synchronize()
-            F.invalidate_packed_weights()    # the weight re-pack must be part of the recording
+            F.invalidate_packed_weights()
+            gemm_mode = _lib.gemm_mode_from_env()
+            if self._pack_weights is not None:
+                # pack once, outside the recording: the cached planes stay valid through the capture (no parameter changes
+                # before the recorded Adam step), so the recorded forward contains no re-pack, and the recorded Adam step
+                # keeps the planes current from then on
+                widths = [self._pack_weights[0].shape[1]] + [W.shape[0] for W in self._pack_weights]
+                self._packed_ptr, self._packed_buf = F._packed_weights(lib, self._pack_weights, widths, gemm_mode, dev)
+                self.optimizer.set_packed_targets(F.packed_weight_targets(self._pack_weights, gemm_mode, self._packed_ptr))
+            # (otherwise the weight re-pack is part of the recording: the cache was just invalidated)
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.clica_launch_count(-1)
             # NCCL's watchdog thread polls CUDA events while the collectives are being recorded: only this thread's
@@ -140,9 +156,16 @@ class GraphedTrainStep:
                 for group in self.optimizer.param_groups:
                     if group.get("_step_state") is not None:
                         group["_step_state"].zero_()
+            if self._pack_weights is not None:
+                F.repack_weights_into(self._packed_ptr, self._pack_weights, gemm_mode)      # planes of the restored weights
             self.stream.synchronize()
         cur.wait_stream(self.stream)
         torch.autograd.graph.increment_version(self.params)
+        self._note_versions()
+
+    def _note_versions(self):
+        if self._pack_weights is not None:
+            self._pack_versions = [W._version for W in self._pack_weights]
 
     # per-step API ----------------------------------------------------------------------------------------------
     def stage(self, z1: torch.Tensor, z2: torch.Tensor) -> None:
@@ -168,10 +191,15 @@ class GraphedTrainStep:
     def replay(self) -> torch.Tensor:
         """One training step on the staged inputs (asynchronous). Returns the device tensor
         ``[loss, pos_mean, neg_mean]`` that the step overwrites."""
+        if self._pack_weights is not None and any(W._version != v for W, v in zip(self._pack_weights, self._pack_versions)):
+            # somebody else changed the weights since the last replay (checkpoint load, manual copy_): the planes the graph
+            # reads are stale -- refresh them before the step
+            F.repack_weights_into(self._packed_ptr, self._pack_weights, _lib.gemm_mode_from_env())
         self.graph.replay()
         self._replayed.record(torch.cuda.current_stream(self.device))
         self.steps_taken += 1
         torch.autograd.graph.increment_version(self.params)     # the graph updated the parameters in place
+        self._note_versions()
         return self.out_dev
 
     def __call__(self, z1: Optional[torch.Tensor] = None, z2: Optional[torch.Tensor] = None) -> torch.Tensor:

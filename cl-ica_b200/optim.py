@@ -22,6 +22,13 @@ class FusedAdam(torch.optim.Optimizer):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, capturable=bool(capturable)))
+        self._packed_targets = None
+
+    def set_packed_targets(self, targets):
+        """``{id(weight): (hi_ptr, lo_ptr, cols, ld)}`` (``functional.packed_weight_targets``): a capturable step then also
+        writes those weights in the encoder GEMMs' operand format, so no re-pack pass follows the update.  ``None``
+        switches it off.  The caller owns the packed buffer and keeps it alive."""
+        self._packed_targets = dict(targets) if targets else None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -67,8 +74,11 @@ class FusedAdam(torch.optim.Optimizer):
                     if pending:
                         state[0] = pending
                     group["_step_state"] = state
+                pack = None
+                if self._packed_targets:
+                    pack = [self._packed_targets.get(id(p)) for p in owners]
                 F.adam_step_capturable(ps, gs, ms, vs, group["lr"], group["betas"][0], group["betas"][1],
-                                       group["eps"], state)
+                                       group["eps"], state, pack=pack)
             else:
                 F.adam_step(ps, gs, ms, vs, group["lr"], group["betas"][0], group["betas"][1], group["eps"], step)
             # the kernel wrote the parameters through raw pointers: tell autograd / the packed-weight cache

@@ -185,6 +185,11 @@ CLICA_API size_t clica_mlp_workspace_bytes(int M, int L, const int* widths, int 
 CLICA_API size_t clica_mlp_packed_weight_bytes(int L, const int* widths, int mode);
 CLICA_API int clica_mlp_pack_weights(int L, const int* widths, const float* const* W, int mode, void* packed,
                   size_t packed_bytes, void* stream);
+/* Where layer l lives inside `packed`: byte offsets of its hi / lo planes (-1: layer not packed / no lo plane) and
+ * the planes' row pitch in floats (columns [widths[l], ld) are zero padding).  For an optimizer that keeps the
+ * planes current itself (clica_adam_step_capturable_packed) instead of re-packing after every step. */
+CLICA_API int clica_mlp_packed_weight_layout(int L, const int* widths, int mode, long long* hi_off,
+                  long long* lo_off, int* ld);
 
 CLICA_API int clica_mlp_fwd(int L, const int* widths, const float* const* W, const float* const* b,
                   float* const* acts, int M, float slope, int mode, const void* packed_weights,
@@ -224,6 +229,16 @@ CLICA_API int clica_adam_step(int n, float* const* params, const float* const* g
 CLICA_API int clica_adam_step_capturable(int n, float* const* params, const float* const* grads,
                     float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel, float lr,
                     float beta1, float beta2, float eps, void* step_state, float grad_scale, void* stream);
+
+/* Same update; tensor k with pack_hi[k] != NULL -- a row-major weight matrix with pack_cols[k] columns -- is ALSO
+ * written in the tensor-core operand format at pack_hi[k] / pack_lo[k] (row pitch pack_ld[k] floats; pack_lo[k]
+ * NULL: one plane with the fp32 value).  Replaces the clica_mlp_pack_weights pass that would otherwise follow
+ * every optimizer step (main_mlp.py:283 followed by the next step's encoder forward). */
+CLICA_API int clica_adam_step_capturable_packed(int n, float* const* params, const float* const* grads,
+                    float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel, float lr,
+                    float beta1, float beta2, float eps, void* step_state, float grad_scale,
+                    float* const* pack_hi, float* const* pack_lo, const int* pack_cols, const int* pack_ld,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Frozen mixing network g of h = f o g (main_mlp.py:313), forward only.
