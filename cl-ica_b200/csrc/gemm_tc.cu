@@ -928,7 +928,7 @@ struct TcPrepared {
     size_t stage_bytes;
     int items;
 };
-int tc_prepare(const TcGemm& g, int sm_count, TcPrepared* out) {
+int tc_prepare(const TcGemm& g, int sm_count, TcPrepared* out, bool in_chain = false) {
     CLICA_REQUIRE(g.Mo >= 1 && g.No >= 1 && g.Kr >= 1, CLICA_E_BADARG, "tc_gemm: empty problem");
     CLICA_REQUIRE(g.A.hi && g.B.hi, CLICA_E_BADARG, "tc_gemm: null operand");
     CLICA_REQUIRE(g.epi != kTcAtomic || g.out != nullptr, CLICA_E_BADARG, "tc_gemm: atomic epilogue needs a plain output");
@@ -941,7 +941,9 @@ int tc_prepare(const TcGemm& g, int sm_count, TcPrepared* out) {
     //   1: always;  2: only where the isolated per-shape timings favoured pairs (tools/gemm_bench.py): weight-gradient
     //   GEMMs always, forward GEMMs wider than one tile, masked backward-data GEMMs with >= 32 k-blocks
     const int pair_mode = env_int("CLICA_TC_PAIR", kPairDefault);
-    bool pair_ok = pair_mode != 0 && g.Mo > BM && sm_count >= 2;
+    // (a GEMM with a single 128-row tile -- e.g. the weight gradient of a 100-wide layer -- still runs as a pair when it is
+    // part of a chain: the peer CTA multiplies TMA zero-fill, which costs less than breaking the chain into three launches)
+    bool pair_ok = pair_mode != 0 && (g.Mo > BM || in_chain) && sm_count >= 2;
     if (pair_ok && pair_mode == 2) {
         if (g.epi == kTcBiasAct) pair_ok = g.No > 128;
         else if (g.epi == kTcMask) pair_ok = ceil_div(g.Kr, BK) >= 32;
@@ -1068,7 +1070,7 @@ int tc_chain_launch(const TcChainLink* links, int n, int sm_count, void* flag_ws
     static thread_local ChainParams P;
     const bool enabled = env_int("CLICA_TC_CHAIN", 1) != 0 && flag_ws != nullptr;
     for (int i = 0; i < n; ++i) {
-        int rc = tc_prepare(links[i].g, sm_count, &pr[i]);
+        int rc = tc_prepare(links[i].g, sm_count, &pr[i], enabled && n > 1);
         if (rc) return rc;
     }
     auto chainable = [&](int i) { return enabled && pr[i].ctas == 2 && !pr[i].conv; };
