@@ -171,6 +171,65 @@ class _LpInfoNCE(torch.autograd.Function):
         return g1, g2, g3, None, None, None, None, None
 
 
+class _LpInfoNCEPairs(torch.autograd.Function):
+    """The training step's own form of the loss: ``ab = [z1_rec; z2_rec]`` as ONE [2B, d] encoder output and the
+    negatives ``z3_rec = roll(z1_rec, 1, 0)`` of main_mlp.py:272 taken as what they are for a sum over all of them -- the
+    rows of ``z1_rec`` in another order.  No roll kernel, no slice / concatenate nodes in the autograd graph: the forward
+    streams ``z1_rec`` itself, the merged backward writes both gradient halves into one [2B, d] tensor."""
+
+    @staticmethod
+    def forward(ctx, ab, p, tau, alpha, include_pos):
+        lib = _lib.load()
+        ab = _as_rows(ab, "encoder output [z1_rec; z2_rec]").contiguous()
+        if ab.shape[0] % 2:
+            raise RuntimeError("lp_infonce_pairs: expected [2B, d] rows (anchors first, then positives)")
+        B, d = ab.shape[0] // 2, ab.shape[1]
+        z1, z2 = ab[:B], ab[B:]
+        dev = ab.device
+        with torch.cuda.device(dev):
+            out = torch.empty(5 * B + 3, dtype=torch.float32, device=dev)
+            rowstat, loss_i, lse, pos, scal = out[:2 * B], out[2 * B:3 * B], out[3 * B:4 * B], out[4 * B:5 * B], out[5 * B:]
+            ws = _workspace(lib.clica_lpnce_workspace_bytes(B, B, d), dev, "lpnce")
+            rc = lib.clica_lpnce_fwd(z1.data_ptr(), d, z2.data_ptr(), d, z1.data_ptr(), d, B, B, d, float(p), float(tau),
+                                     float(alpha), int(include_pos), 1, loss_i.data_ptr(), lse.data_ptr(), pos.data_ptr(),
+                                     rowstat.data_ptr(), scal.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            _lib.check(rc, "clica_lpnce_fwd")
+        ctx.save_for_backward(ab, rowstat, pos)
+        ctx.cfg = (float(p), float(tau), float(alpha), int(include_pos))
+        ctx.set_materialize_grads(False)
+        mean, pos_mean, neg_mean = scal[0], scal[1], scal[2]
+        ctx.mark_non_differentiable(loss_i, pos_mean, neg_mean)
+        return mean, loss_i, pos_mean, neg_mean
+
+    @staticmethod
+    def backward(ctx, g_mean, _g_li, _g_pos, _g_neg):
+        if g_mean is None or not ctx.needs_input_grad[0]:
+            return (None,) * 5
+        lib = _lib.load()
+        ab, rowstat, pos = ctx.saved_tensors
+        p, tau, alpha, include_pos = ctx.cfg
+        B, d = ab.shape[0] // 2, ab.shape[1]
+        dev = ab.device
+        with torch.cuda.device(dev):
+            g = torch.empty_like(ab)
+            g_mean = g_mean.to(device=dev, dtype=torch.float32).contiguous()
+            ws = _workspace(lib.clica_lpnce_bwd_sharded_workspace_bytes(B, B, d), dev, "lpnce_bwd")
+            z1, z2 = ab[:B], ab[B:]
+            rc = lib.clica_lpnce_bwd_sharded(z1.data_ptr(), d, z2.data_ptr(), d, z1.data_ptr(), d, rowstat.data_ptr(),
+                                             pos.data_ptr(), B, B, d, 0, p, tau, alpha, include_pos, g_mean.data_ptr(),
+                                             g[:B].data_ptr(), d, g[B:].data_ptr(), d, ws.data_ptr(), ws.numel(),
+                                             _stream_ptr(dev))
+            _lib.check(rc, "clica_lpnce_bwd_sharded")
+        return g, None, None, None, None
+
+
+def lp_infonce_pairs(ab, p, tau=1.0, alpha=0.5, include_pos=True):
+    """Fused Lp-InfoNCE (``p = 0``: dot-product similarity) of ``ab = [z1_rec; z2_rec]`` with every anchor as a negative
+    (= the reference's ``z3_rec = roll(z1_rec, 1, 0)``, main_mlp.py:272).  Returns ``(mean, per_item, pos_mean,
+    neg_mean)``; only ``mean`` carries grad."""
+    return _LpInfoNCEPairs.apply(ab, p, tau, alpha, include_pos)
+
+
 def is_row_roll_of(z3, z1) -> bool:
     """True when autograd itself says ``z3 = torch.roll(z1, k, 0)`` (the reference's negatives, main_mlp.py:272)."""
     fn = getattr(z3, "grad_fn", None)

@@ -74,6 +74,15 @@ class GraphedTrainStep:
             plan = f._plan()
             if plan is not None and all(l.weight.requires_grad for l in plan[0]):
                 self._pack_weights = [l.weight for l in plan[0]]
+        # (p, tau, alpha, include_pos) when the criterion is one of the two fused losses inside the kernels' domain
+        self._pairs_cfg = None
+        if os.environ.get("CLICA_GRAPH_PAIRS", "1") == "1":
+            name = type(criterion).__name__
+            if name == "LpSimCLRLoss" and getattr(criterion, "pow", True) and float(getattr(criterion, "p", 0)) >= 1.0:
+                self._pairs_cfg = (float(criterion.p), float(criterion.tau), float(criterion.alpha),
+                                   bool(criterion.simclr_compatibility_mode))
+            elif name == "SimCLRLoss" and not getattr(criterion, "normalize", False):
+                self._pairs_cfg = (0.0, float(criterion.tau), float(criterion.alpha), True)
         dev = self.device
         self.z_dev = torch.zeros((2 * self.B, self.n), dtype=torch.float32, device=dev)
         self.out_dev = torch.zeros(3, dtype=torch.float32, device=dev)
@@ -97,6 +106,16 @@ class GraphedTrainStep:
         else:
             x = self.g(self.z_dev)
         ab = self.f(x)
+        if self.world == 1 and self._pairs_cfg is not None and ab.shape == (2 * self.B, ab.shape[-1]) and ab.shape[-1] <= 320:
+            # anchors and positives as one tensor, the anchors themselves as the (rolled) negatives: one forward and one
+            # backward launch with no roll / slice / concatenate kernels around them
+            total, _, pos_mean, neg_mean = F.lp_infonce_pairs(ab, *self._pairs_cfg)
+            total.backward()
+            self.optimizer.step()
+            torch.stack([total.detach(), pos_mean, neg_mean], out=self.out_dev)
+            if self.host_io:
+                self.out_host.copy_(self.out_dev, non_blocking=True)
+            return
         a, b = ab[:self.B], ab[self.B:]
         if self.world > 1:
             from . import sharded
@@ -207,12 +226,21 @@ class GraphedTrainStep:
             self.stage(z1, z2)
         return self.replay()
 
-    def step_host(self, z1: torch.Tensor, z2: torch.Tensor) -> Tuple[float, float, float]:
+    def pinned_inputs(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The two [B, n] halves of the pinned staging buffer the graph's host->device copy reads.  A producer (sampler,
+        data loader) that writes the batch straight into them saves the host-side staging copy: call ``step_host()``
+        without arguments afterwards.  They may be overwritten as soon as ``step_host`` has returned."""
+        if not self.host_io:
+            raise RuntimeError("pinned_inputs needs host_io=True")
+        return self.z_host[:self.B], self.z_host[self.B:]
+
+    def step_host(self, z1: Optional[torch.Tensor] = None, z2: Optional[torch.Tensor] = None) -> Tuple[float, float, float]:
         """Host tensors in, host floats out (what ``main_mlp.py:285`` reads with ``.item()``): stage, replay,
-        wait for the graph's own device->host copy."""
+        wait for the graph's own device->host copy.  Without arguments the batch is taken from ``pinned_inputs()``."""
         if not self.host_io:
             raise RuntimeError("step_host needs host_io=True")
-        self.stage(z1, z2)
+        if z1 is not None:
+            self.stage(z1, z2)
         self.replay()
         torch.cuda.current_stream(self.device).synchronize()
         o = self.out_host

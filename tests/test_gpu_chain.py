@@ -153,3 +153,27 @@ def test_graphed_step_survives_external_weight_changes(cuda_device):
     for a, b in zip(f1.parameters(), f2.parameters()):
         assert (a - b).abs().mean().item() <= 1e-5
         assert (a - b).abs().max().item() <= 7e-3
+
+
+@pytest.mark.parametrize("p,d,B", [(2, 10, 1000), (3, 40, 515), (1, 5, 256), (0, 10, 768), (2.5, 16, 300)])
+def test_pairs_form_equals_the_rolled_call(p, d, B, cuda_device):
+    """lp_infonce_pairs([z1; z2]) -- anchors streamed as their own negatives, both gradient halves in one tensor -- against
+    the reference-shaped call lp_infonce(z1, z2, roll(z1, 1, 0)) of main_mlp.py:270-280 (same negative set, other order)."""
+    from clica_b200 import functional as F
+    g = torch.Generator().manual_seed(int(10 * p) + d + B)
+    z1 = torch.randn(B, d, generator=g)
+    z1 = z1 / z1.norm(dim=-1, keepdim=True)
+    z2 = z1 + 0.05 * torch.randn(B, d, generator=g)
+    ab = torch.cat([z1, z2], 0).to(cuda_device).requires_grad_(True)
+    a = z1.to(cuda_device).requires_grad_(True)
+    b = z2.to(cuda_device).requires_grad_(True)
+    m0, li0, pos0, neg0 = F.lp_infonce(a, b, torch.roll(a, 1, 0), float(p), 0.7, 0.5, True)
+    m1, li1, pos1, neg1 = F.lp_infonce_pairs(ab, float(p), 0.7, 0.5, True)
+    (3.0 * m0).backward()
+    (3.0 * m1).backward()
+    assert abs(m0.item() - m1.item()) <= 2e-6 * max(1.0, abs(m0.item()))
+    assert torch.allclose(li0, li1, rtol=0, atol=5e-6 * max(1.0, li0.abs().max().item()))
+    assert abs(pos0.item() - pos1.item()) <= 1e-6 * max(1.0, abs(pos0.item())) and abs(neg0.item() - neg1.item()) <= 2e-6 * max(1.0, abs(neg0.item()))
+    scale = max(a.grad.abs().max().item(), b.grad.abs().max().item())
+    assert (ab.grad[:B] - a.grad).abs().max().item() <= 2e-5 * scale
+    assert (ab.grad[B:] - b.grad).abs().max().item() <= 2e-5 * scale
