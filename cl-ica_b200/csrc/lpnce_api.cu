@@ -147,7 +147,11 @@ int occ_bwd(int pc, Shape sh) {
 // Forward variant with 4 owner rows per thread (dot form, p = 2, d <= 10): CLICA_LPNCE_R4 (default on)
 int fwd_r4_enabled() { return env_flag("CLICA_LPNCE_R4", 1) != 0; }
 // dot-form bound (see lpnce_kernels.cuh); CLICA_LPNCE_DOT=0 disables the form
-float dot_limit() { return env_flag("CLICA_LPNCE_DOT", 1) != 0 ? 8.0f : 0.f; }
+float dot_limit() {
+    if (env_flag("CLICA_LPNCE_DOT", 1) == 0) return 0.f;
+    const int tenths = env_flag("CLICA_LPNCE_DOT_LIMIT_X10", 80);      // the bound in tenths (default 8.0)
+    return tenths > 0 ? 0.1f * (float)tenths : 0.f;
+}
 // backward: measured on B200 (profiles/r2_loss_probe.md) the dot form is SLOWER there than subtract-then-square (the
 // weights need both operands anyway and the kernel is latency-bound at 16 warps per SM), so it is opt-in
 float dot_limit_bwd() { return env_flag("CLICA_LPNCE_DOT_BWD", 0) != 0 ? dot_limit() : 0.f; }

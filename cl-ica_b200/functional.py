@@ -22,7 +22,11 @@ _retired = []          # outgrown workspaces, kept alive (see _workspace)
 
 # ---- gradient synchronisation hook of the encoder backward (multi-GPU) ----------------------------------
 _grad_sync = None
-GRAD_BUCKET_BYTES = 2 << 20          # CLICA_GRAD_BUCKET_MB overrides (read when a backward runs)
+# Gradient buckets of the multi-GPU step (CLICA_GRAD_BUCKET_MB overrides, read when a backward runs).  Measured on 8 x B200
+# at BASELINE config 3 (profiles/r2_n8_allreduce_tuning.md): ONE bucket -- the whole backward as one chained launch, then
+# one all-reduce -- beats 2 MB / 12 MB buckets (1.58 vs 1.76 / 1.66 ms per step): NCCL's CTAs cannot run beside the
+# persistent one-CTA-per-SM GEMM grid, so "overlapped" buckets only break the chain without hiding the transfer.
+GRAD_BUCKET_BYTES = 1 << 40
 
 
 class grad_sync:
