@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) sampler_kernel(const SampleParams q) {
         o[c] = v;
     }
     if (q.space == 1) {
-        const float inv = rsqrtf(nrm);
+        const float inv = 1.f / sqrtf(nrm);               // IEEE sqrt + divide: the reference asserts | |z| - 1 | <= 1e-5 on these rows
         for (int c = 0; c < q.n; ++c) o[c] *= inv;
     }
 }
