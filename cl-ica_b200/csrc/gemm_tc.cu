@@ -857,7 +857,7 @@ int get_tensor_map(const float* ptr, int rows, int cols, int ld, int box_rows, b
 
 }  // namespace
 
-// Tile width and split-K factor.  Measured (tools/gemm_phase_probe.py): once the ring is flowing, a CTA's main loop
+// Tile width and split-K factor.  Measured in round 1 (clock64 phase stamps): once the ring is flowing, a CTA's main loop
 // is paced by the operand bytes it pulls through the TMA (~95-105 GB/s per SM whether 96 or 148 CTAs run), not by
 // the tensor pipe, so an item costs  kb * (BM + BN) * BK * 4 * planes  bytes of loads plus an epilogue that moves
 // BM * BN * 4 * planes output bytes (weighted x4: write / reduce traffic drains slower than loads stream), and
