@@ -33,6 +33,27 @@ from . import functional as F
 from .optim import FusedAdam
 
 
+def pairs_config(criterion):
+    """``(p, tau, alpha, include_pos)`` for ``functional.lp_infonce_pairs`` when ``criterion`` is one of the two fused
+    losses with arguments inside the kernels' domain -- ``LpSimCLRLoss`` with ``p >= 1`` and ``pow=True``
+    (losses.py:416-431), or ``SimCLRLoss`` without ``normalize`` (losses.py:172-175; p = 0 selects the dot-product form)
+    -- else ``None`` (the criterion is then called the way the script calls it)."""
+    name = type(criterion).__name__
+    try:
+        if name == "LpSimCLRLoss":
+            if not getattr(criterion, "pow", True) or float(criterion.p) < 1.0:
+                return None
+            return (float(criterion.p), float(criterion.tau), float(criterion.alpha),
+                    bool(criterion.simclr_compatibility_mode))
+        if name == "SimCLRLoss":
+            if getattr(criterion, "normalize", False):
+                return None
+            return (0.0, float(criterion.tau), float(criterion.alpha), True)
+    except (AttributeError, TypeError, ValueError):
+        return None
+    return None
+
+
 class GraphedTrainStep:
     def __init__(self, f: torch.nn.Module, g: Optional[torch.nn.Module], criterion, batch_size: int, n_in: int,
                  lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, host_io: bool = True,
@@ -74,15 +95,7 @@ class GraphedTrainStep:
             plan = f._plan()
             if plan is not None and all(l.weight.requires_grad for l in plan[0]):
                 self._pack_weights = [l.weight for l in plan[0]]
-        # (p, tau, alpha, include_pos) when the criterion is one of the two fused losses inside the kernels' domain
-        self._pairs_cfg = None
-        if os.environ.get("CLICA_GRAPH_PAIRS", "1") == "1":
-            name = type(criterion).__name__
-            if name == "LpSimCLRLoss" and getattr(criterion, "pow", True) and float(getattr(criterion, "p", 0)) >= 1.0:
-                self._pairs_cfg = (float(criterion.p), float(criterion.tau), float(criterion.alpha),
-                                   bool(criterion.simclr_compatibility_mode))
-            elif name == "SimCLRLoss" and not getattr(criterion, "normalize", False):
-                self._pairs_cfg = (0.0, float(criterion.tau), float(criterion.alpha), True)
+        self._pairs_cfg = pairs_config(criterion) if os.environ.get("CLICA_GRAPH_PAIRS", "1") == "1" else None
         dev = self.device
         self.z_dev = torch.zeros((2 * self.B, self.n), dtype=torch.float32, device=dev)
         self.out_dev = torch.zeros(3, dtype=torch.float32, device=dev)
