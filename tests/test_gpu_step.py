@@ -52,7 +52,10 @@ def test_three_adam_steps_match_the_reference(cuda_device):
                 ref = g["grad0_head_" + k]
                 got = prm.grad.detach().cpu().numpy().ravel()[:8]
                 scale = np.sqrt(g["grad0_digest_" + k][2] / prm.numel()) + 1e-30      # rms of the reference grad
-                assert np.abs(got - ref).max() <= 2e-3 * scale + 1e-10, k   # (the last bias' gradient is analytically 0)
+                ratio = np.abs(got - ref).max() / (scale + 1e-30)
+                # measured on B200: <= 1e-4 of the gradient's rms for every parameter (3xTF32 encoder, fused loss); the last
+                # bias' gradient is analytically 0
+                assert np.abs(got - ref).max() <= 1e-4 * scale + 1e-10, (k, ratio)
         opt.step()
         rec = g["losses"][step]
         assert abs(total.item() - rec[0]) <= 5e-6 * max(1.0, abs(rec[0]))
