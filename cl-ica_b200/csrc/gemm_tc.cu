@@ -54,6 +54,8 @@ struct TcKernelParams {
     uint32_t mn_lbo, mn_sbo, mn_lt;   // MN-major descriptor fields (defaults: BK*128, 512, 1)
     float* colsum;                    // optional [No]: += column sums of the stored values (pre-zeroed by the caller)
     int out_tma;                      // kTcAtomic: tmOh describes `out`, partial sums leave as TMA reduce-adds
+    int kchunk;                       // > 0: the tensor core accumulates at most this many k-blocks into one TMEM accumulator;
+                                      // the epilogue warps add the chunks' partial sums in fp32 registers (see the MMA issuer)
 };
 
 // One launch runs a CHAIN of GEMMs (the hidden layers of the encoder forward, or the dX / dW GEMMs of its backward) as
@@ -434,9 +436,9 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
     } else if (warp == 1) {
         if (lane == 0 && cta_rank == 0) {
             // ===== MMA issuer (pair mode: the leader CTA drives both tensor cores) =====
-            uint32_t it = 0, tile_iter = 0;
+            uint32_t it = 0, acc_iter = 0;          // acc_iter: uses of the two TMEM accumulator buffers so far
             int gi = 0;
-            for (int w = unit_id; w < total; w += num_units, ++tile_iter) {
+            for (int w = unit_id; w < total; w += num_units) {
                 while (gi + 1 < P.n && w >= P.g[gi + 1].item_begin) ++gi;
                 const ChainGemm& G = P.g[gi];
                 const TcKernelParams q = G.q;            // by value: registers, not re-read after every asm memory clobber
@@ -447,41 +449,49 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
                 const uint32_t a_lbo = q.a_mn ? q.mn_lbo : 16u, b_lbo = q.b_mn ? q.mn_lbo : 16u;
                 const uint32_t a_sbo = q.a_mn ? q.mn_sbo : 1024u, b_sbo = q.b_mn ? q.mn_sbo : 1024u;
                 const uint32_t a_lt = q.a_mn ? q.mn_lt : 2u, b_lt = q.b_mn ? q.mn_lt : 2u;
-                const uint32_t as = tile_iter & 1u;
-                mbar_wait(&tmem_empty_bar[as], ((tile_iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
-                tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + as * kAccCols;
                 const uint32_t idesc = make_idesc(q.a_mn, q.b_mn, tile_width<CTAS>(G.bn, q.No - im.n_idx * G.bn), BM * CTAS);
-                for (int kb = im.kb0; kb < im.kb1; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)stages;
-                    const uint32_t ph = (it / (uint32_t)stages) & 1u;
-                    if constexpr (!CONV) mbar_wait(&full_bar[s], ph);
-                    else if constexpr (CTAS == 1) mbar_wait(&ready_bar[s], ph);
-                    else mbar_wait_cluster(&ready_bar[s], ph);
+                // K chunks: the tensor core's fp32 accumulator TRUNCATES when it aligns addends, a bias that grows with the
+                // number of MMAs accumulated in TMEM (K = 2000: 756 of them, ~6e-5 through the encoder stack).  With
+                // q.kchunk > 0 every kchunk k-blocks go to the OTHER accumulator buffer and the epilogue warps add the
+                // finished chunk into fp32 registers (rounded adds) while the next chunk is being multiplied.
+                const int kc = (q.kchunk > 0) ? q.kchunk : (im.kb1 - im.kb0);
+                for (int c0 = im.kb0; c0 < im.kb1; c0 += kc, ++acc_iter) {
+                    const int c1 = min(im.kb1, c0 + kc);
+                    const uint32_t as = acc_iter & 1u;
+                    mbar_wait(&tmem_empty_bar[as], ((acc_iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
                     tcgen05_fence_after();
-                    const uint32_t sa = tiles + s * P.stage_stride;
-                    const uint32_t a_hi = sa, a_lo = sa + kABytes;
-                    const uint32_t b_hi = sa + nplanes * kABytes, b_lo = b_hi + kBBytes;
+                    const uint32_t tmem_acc = tmem_base + as * kAccCols;
+                    for (int kb = c0; kb < c1; ++kb, ++it) {
+                        const uint32_t s = it % (uint32_t)stages;
+                        const uint32_t ph = (it / (uint32_t)stages) & 1u;
+                        if constexpr (!CONV) mbar_wait(&full_bar[s], ph);
+                        else if constexpr (CTAS == 1) mbar_wait(&ready_bar[s], ph);
+                        else mbar_wait_cluster(&ready_bar[s], ph);
+                        tcgen05_fence_after();
+                        const uint32_t sa = tiles + s * P.stage_stride;
+                        const uint32_t a_hi = sa, a_lo = sa + kABytes;
+                        const uint32_t b_hi = sa + nplanes * kABytes, b_lo = b_hi + kBBytes;
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint32_t first = (kb > im.kb0 || ks > 0) ? 1u : 0u;
-                        const uint64_t dah = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
-                        const uint64_t dbh = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
-                        if (nplanes == 2) {
-                            const uint64_t dal = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
-                            const uint64_t dbl = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-                            umma_tf32<CTAS>(tmem_acc, dal, dbh, idesc, first);   // small terms first
-                            umma_tf32<CTAS>(tmem_acc, dah, dbl, idesc, 1u);
-                            umma_tf32<CTAS>(tmem_acc, dah, dbh, idesc, 1u);
-                        } else {
-                            umma_tf32<CTAS>(tmem_acc, dah, dbh, idesc, first);
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const uint32_t first = (kb > c0 || ks > 0) ? 1u : 0u;
+                            const uint64_t dah = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
+                            const uint64_t dbh = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+                            if (nplanes == 2) {
+                                const uint64_t dal = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+                                const uint64_t dbl = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+                                umma_tf32<CTAS>(tmem_acc, dal, dbh, idesc, first);   // small terms first
+                                umma_tf32<CTAS>(tmem_acc, dah, dbl, idesc, 1u);
+                                umma_tf32<CTAS>(tmem_acc, dah, dbh, idesc, 1u);
+                            } else {
+                                umma_tf32<CTAS>(tmem_acc, dah, dbh, idesc, first);
+                            }
                         }
+                        // stage reusable once these MMAs have read it (pair mode: in both CTAs)
+                        if constexpr (CTAS == 1) umma_commit(&empty_bar[s]); else umma_commit_pair(&empty_bar[s]);
                     }
-                    // stage reusable once these MMAs have read it (pair mode: in both CTAs)
-                    if constexpr (CTAS == 1) umma_commit(&empty_bar[s]); else umma_commit_pair(&empty_bar[s]);
+                    // accumulator (chunk) complete (pair mode: each CTA's epilogue drains its own 128 TMEM lanes)
+                    if constexpr (CTAS == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_pair(&tmem_full_bar[as]);
                 }
-                // accumulator complete (pair mode: each CTA's epilogue drains its own 128 TMEM lanes)
-                if constexpr (CTAS == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_pair(&tmem_full_bar[as]);
             }
         }
     } else if (CONV && warp >= 10) {
@@ -585,9 +595,10 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
             for (int r = 0; r < 32; ++r) t += *reinterpret_cast<const float*>(sbuf + r * 128 + ((cw ^ (uint32_t)(r & 7)) << 4) + ci);
             return t;
         };
-        uint32_t tile_iter = 0;
+        uint32_t acc_iter = 0;                  // uses of the two TMEM accumulator buffers so far (same count as the MMA issuer's)
+        float ksum[(kMaxBN / 64) * 32];          // K-chunked items: this thread's running sums (4 column chunks x 32 columns)
         int gi = 0;
-        for (int w = unit_id; w < total; w += num_units, ++tile_iter) {
+        for (int w = unit_id; w < total; w += num_units) {
             while (gi + 1 < P.n && w >= P.g[gi + 1].item_begin) ++gi;
             const ChainGemm& G = P.g[gi];
             const TcKernelParams q = G.q;            // by value: registers, not re-read after every asm memory clobber
@@ -598,7 +609,6 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
             const bool aux_vec = (q.aux != nullptr) && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15u) == 0);
             const int m0 = im.m_idx * (BM * CTAS) + (int)cta_rank * BM;
             const int n0 = im.n_idx * bn;
-            const uint32_t as = tile_iter & 1u;
             const int row = m0 + wq * 32 + lane;
             const bool row_ok = row < q.Mo;
             const int rowc = row_ok ? row : (q.Mo - 1);         // clamped: loads stay in bounds, stores are predicated
@@ -626,13 +636,52 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
             };
             const bool use_aux = (q.epi == kTcMask) && (q.aux != nullptr) && !(P.debug & 4);
             if (use_aux) load_aux(half);
-            mbar_wait(&tmem_full_bar[as], (tile_iter >> 1) & 1u);
-            tcgen05_fence_after();
+            // K-chunked item (see the MMA issuer): add every finished chunk of k-blocks into fp32 registers and hand its
+            // accumulator buffer straight back; the epilogue below then works on the register sums
+            const int kc = (q.kchunk > 0) ? q.kchunk : (im.kb1 - im.kb0);
+            const bool multi = (im.kb1 - im.kb0) > kc;
+            uint32_t as = acc_iter & 1u;
+            if (multi) {
+                for (int c0 = im.kb0; c0 < im.kb1; c0 += kc, ++acc_iter) {
+                    const uint32_t asc = acc_iter & 1u;
+                    mbar_wait(&tmem_full_bar[asc], (acc_iter >> 1) & 1u);
+                    tcgen05_fence_after();
+                    int ci = 0;
 #pragma unroll 1
-            for (int chunk = half; chunk < bn / 32; chunk += 2) {
+                    for (int chunk = half; chunk < bn / 32; chunk += 2, ++ci) {
+                        float t[32];
+                        __syncwarp();
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + asc * kAccCols + (uint32_t)(chunk * 32), t);
+                        if (c0 == im.kb0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) ksum[ci * 32 + j] = t[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) ksum[ci * 32 + j] += t[j];
+                        }
+                    }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CTAS == 1) mbar_arrive(&tmem_empty_bar[asc]);
+                        else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[asc]), 0u));
+                    }
+                }
+            } else {
+                mbar_wait(&tmem_full_bar[as], (acc_iter >> 1) & 1u);
+                tcgen05_fence_after();
+            }
+            int ci_out = 0;
+#pragma unroll 1
+            for (int chunk = half; chunk < bn / 32; chunk += 2, ++ci_out) {
                 float v[32];
                 __syncwarp();   // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
-                tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + as * kAccCols + (uint32_t)(chunk * 32), v);
+                if (multi) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ksum[ci_out * 32 + j];
+                } else {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + as * kAccCols + (uint32_t)(chunk * 32), v);
+                }
                 const int col0 = n0 + chunk * 32;
                 const int nvalid = min(32, q.No - col0);
                 if (q.epi == kTcBiasAct) {
@@ -709,12 +758,15 @@ gemm_tc_kernel(const __grid_constant__ ChainParams P) {
                 }
                 if (want_sum && lane < nvalid) atomicAdd(q.colsum + col0 + lane, csum);
             }
-            // this warp has read its share of the accumulator: hand it back to the MMA warp
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (CTAS == 1) mbar_arrive(&tmem_empty_bar[as]);
-                else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0u));
+            // this warp has read its share of the accumulator: hand it back to the MMA warp (K-chunked items did so per chunk)
+            if (!multi) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CTAS == 1) mbar_arrive(&tmem_empty_bar[as]);
+                    else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0u));
+                }
+                ++acc_iter;
             }
             if (publish) {
                 // a later GEMM of the chain reads these rows: once every epilogue warp's stores are complete (not merely
@@ -987,6 +1039,15 @@ int tc_prepare(const TcGemm& g, int sm_count, TcPrepared* out, bool in_chain = f
     q.kb_per_split = ceil_div(q.kb_total, splits);
     splits = ceil_div(q.kb_total, q.kb_per_split);
     q.splits = splits;
+    // K-chunked accumulation (3xTF32 only, reductions of >= 3 chunks only): CLICA_TC_KCHUNK k-blocks per TMEM accumulator
+    // (0: off).  Measured at n = 40 (tools/n40_accuracy.py; error through the 7-layer stack relative to the tensor max,
+    // output / input gradient / worst dW): off 1.1e-5 / 4.8e-5 / 4.8e-5, 16 k-blocks 3.7e-6 / 1.4e-5 / 1.6e-5, 8: 2.6e-6 /
+    // 8e-6 / 1.4e-5, 4: 1.1e-6 / 4e-6 / 6e-6; cost at config 3 (every drain reads TMEM while the tensor core writes the
+    // other buffer): 16 -> +6 %, 8 -> +13 % per step.  n = 10 (K <= 500: 16 k-blocks) is not chunked.
+    {
+        const int kc = env_int("CLICA_TC_KCHUNK", 16);
+        q.kchunk = (nterms == 3 && kc > 0 && q.kb_per_split >= 3 * kc) ? kc : 0;
+    }
     cg.bn = bn;
     cg.num_m = ceil_div(g.Mo, BM * ctas);
     cg.num_n = ceil_div(g.No, bn);

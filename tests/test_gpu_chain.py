@@ -73,7 +73,7 @@ def test_chained_stack_against_the_fp64_oracle(n, M, cuda_device, monkeypatch):
     y, gx, gp = _run_stack(f, torch.tensor(x, device=cuda_device), torch.tensor(gy, device=cuda_device))
     y_ref, acts, pre = mlp_oracle.mlp_forward(x, Ws, bs, slope=0.01)
     dWs, dbs, gx_ref = mlp_oracle.mlp_backward(gy, Ws, acts, pre, slope=0.01, need_dx=True)
-    tol = 5e-5 if n <= 16 else 2e-4                           # 3xTF32 through 7 layers (tolerances)
+    tol = 5e-5 if n <= 16 else 3e-5                           # 3xTF32 through 7 layers (tolerances)
     assert _rel(y.cpu().numpy(), y_ref) <= tol
     assert _rel(gx.cpu().numpy(), gx_ref) <= tol
     for l in range(len(Ws)):

@@ -99,11 +99,13 @@ def test_encoder_stack_against_numpy_oracle(mode_name, n, M, cuda_device):
         assert _rel(bs[l].grad.cpu().numpy(), dbs[l]) <= tol, f"db{l}"
 
 
-@pytest.mark.parametrize("mode_name,tol", [("fp32", 2e-5), ("3xtf32", 2e-4)])
+@pytest.mark.parametrize("mode_name,tol", [("fp32", 2e-5), ("3xtf32", 3e-5)])
 def test_encoder_stack_n40(mode_name, tol, cuda_device):
     """BASELINE config 3's encoder (n = 40: 40 -> 400 -> 2000 x4 -> 400 -> 40).  The first / last layers take the
     KMAX = 48 skinny kernels; the 2000-wide tensor-core layers accumulate 63 k-blocks, where the tensor core's
-    truncating fp32 accumulator costs 3xTF32 a few 1e-5 (stated tolerance 2e-4; exact-fp32 mode 2e-5)."""
+    truncating fp32 accumulator would cost 3xTF32 ~5e-5: the kernel therefore accumulates at most 16 k-blocks in TMEM and
+    adds the chunks in fp32 registers (gemm_tc.cu, CLICA_TC_KCHUNK): measured 1.4e-5 / 1.7e-5, stated 3e-5; exact-fp32
+    mode 2e-5."""
     from clica_b200 import functional as F
     from oracle import mlp_oracle
     mode = MODES[mode_name][0]
