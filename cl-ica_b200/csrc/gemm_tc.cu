@@ -82,7 +82,7 @@ struct ChainParams {
     int n, total_items, stages;
     uint32_t stage_stride;            // bytes between ring stages (the widest GEMM's stage)
     unsigned* flags; int flag_stride; // [n][flag_stride] arrival counters, zero at launch
-    unsigned* err;                    // set when a dependency wait timed out (logic error; the kernel never hangs)
+    unsigned* err;                    // set, and the kernel trapped, when a dependency wait timed out (logic error: fail loudly)
     int debug;                        // CLICA_TC_DEBUG bits (timing experiments only; results are wrong): 1 no output stores,
                                       // 2 no column sums, 4 no mask loads
 };
@@ -310,7 +310,10 @@ __device__ __forceinline__ void wait_blocks(const ChainParams& P, const ChainGem
         const long long t0 = clock64();
         while (ld_acquire_u32(f + b) < need) {
             __nanosleep(32);
-            if (clock64() - t0 > (1LL << 32)) { atomicExch(P.err, 1u); break; }     // ~2 s: a logic error must not hang the device
+            if (clock64() - t0 > (1LL << 35)) {      // ~18 s of SM clocks: a logic error must neither hang the device nor pass silently
+                atomicExch(P.err, 1u);
+                __trap();                             // the launch fails; the next CUDA call of the host reports it
+            }
         }
     }
     fence_proxy_async_all();       // the acquire above (generic proxy) orders the TMA reads (async proxy) that follow

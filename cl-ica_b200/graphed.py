@@ -159,7 +159,7 @@ class GraphedTrainStep:
                 self._body()
             self.stream.synchronize()
             F.invalidate_packed_weights()
-            gemm_mode = _lib.gemm_mode_from_env()
+            gemm_mode = self._gemm_mode = _lib.gemm_mode_from_env()      # the recording is tied to this numeric mode
             if self._pack_weights is not None:
                 # pack once, outside the recording: the cached planes stay valid through the capture (no parameter changes
                 # before the recorded Adam step), so the recorded forward contains no re-pack, and the recorded Adam step
@@ -226,7 +226,7 @@ class GraphedTrainStep:
         if self._pack_weights is not None and any(W._version != v for W, v in zip(self._pack_weights, self._pack_versions)):
             # somebody else changed the weights since the last replay (checkpoint load, manual copy_): the planes the graph
             # reads are stale -- refresh them before the step
-            F.repack_weights_into(self._packed_ptr, self._pack_weights, _lib.gemm_mode_from_env())
+            F.repack_weights_into(self._packed_ptr, self._pack_weights, self._gemm_mode)
         self.graph.replay()
         self._replayed.record(torch.cuda.current_stream(self.device))
         self.steps_taken += 1
