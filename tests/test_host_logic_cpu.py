@@ -66,3 +66,63 @@ def test_pairs_config_only_for_criteria_inside_the_kernels_domain():
     assert pairs_config(SimCLRLoss(False, 0.5)) == (0.0, 0.5, 0.5, True)
     assert pairs_config(SimCLRLoss(True)) is None             # normalisation stays torch code in front of the kernel
     assert pairs_config(Other()) is None
+
+
+def _reference_spaces():
+    """The reference's spaces.py (the checkout, or the read-only copy build() vendors); None when neither is present."""
+    import importlib.util
+    import warnings
+    for d in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        path = os.path.join(d, "spaces.py")
+        if os.path.isfile(path):
+            sys.path.insert(0, d)                    # spaces.py imports spaces_utils / vmf by bare name
+            try:
+                spec = importlib.util.spec_from_file_location("_ref_spaces_for_test", path)
+                mod = importlib.util.module_from_spec(spec)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore", SyntaxWarning)
+                    spec.loader.exec_module(mod)
+                return mod
+            finally:
+                sys.path.remove(d)
+    return None
+
+
+def test_sampler_classes_keep_the_reference_surface_and_delegate_on_cpu():
+    """clica_b200.samplers: same constructors / attributes as spaces.py:47-351; for a CPU device every draw
+    is the reference's own method (bit-identical under the same seed); the module object re-exports the other names."""
+    import torch
+    from clica_b200 import samplers
+    ref = _reference_spaces()
+    if ref is None:
+        pytest.skip("no reference checkout reachable")
+    mod = samplers.build_module(ref)
+    assert mod.__clica_device_samplers__ and mod.Space is ref.Space
+    for name in ("NRealSpace", "NSphereSpace", "NBoxSpace"):
+        assert issubclass(getattr(mod, name), getattr(ref, name)) and getattr(mod, name) is not getattr(ref, name)
+    ours, theirs = mod.NSphereSpace(7), ref.NSphereSpace(7)
+    assert (ours.n, ours.r, ours.dim) == (theirs.n, theirs.r, theirs.dim)
+    torch.manual_seed(5)
+    a = ours.uniform(64, device="cpu")
+    torch.manual_seed(5)
+    b = theirs.uniform(64, device="cpu")
+    assert torch.equal(a, b)
+    torch.manual_seed(6)
+    a2 = ours.normal(a, 0.05, 64, device="cpu")
+    torch.manual_seed(6)
+    b2 = theirs.normal(b, 0.05, 64, device="cpu")
+    assert torch.equal(a2, b2)
+    box_o, box_t = mod.NBoxSpace(4, -1.0, 1.0), ref.NBoxSpace(4, -1.0, 1.0)
+    torch.manual_seed(7)
+    c = box_o.uniform(32, device="cpu")
+    torch.manual_seed(7)
+    d = box_t.uniform(32, device="cpu")
+    assert torch.equal(c, d) and c.min() >= -1 and c.max() <= 1
+    real_o, real_t = mod.NRealSpace(3), ref.NRealSpace(3)
+    torch.manual_seed(8)
+    e = real_o.normal(torch.zeros(3), 0.5, 16, device="cpu")
+    torch.manual_seed(8)
+    f = real_t.normal(torch.zeros(3), 0.5, 16, device="cpu")
+    assert torch.equal(e, f)
+    # tensor-valued scales stay with the reference even for a CUDA device string (no kernel for them)
+    assert samplers._scalar(0.05) and not samplers._scalar(torch.ones(3))
